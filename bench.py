@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- Newton iterations / second (assembly + block solve) of the damped BVP hot path on B200.
+
+Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line on rank 0.
+  * a "step" is ONE damped Newton iteration of try_main_loop_damped's body
+    (src/numerical/BVP_Damp/NR_Damp_solver_damped.rs:2048-2140) WITH a Jacobian refresh: fused F+J assembly,
+    factorisation, the undamped step solve, >= 1 damping trial (F assembly + solve), all reductions.
+  * N = 1 workload: BASELINE.json configs[1] ("c2": 2-variable BVP, 10^6 mesh points).  ``--workload c3`` times
+    configs[2] (12-variable flame, 10^6 points).  N > 1: weak scaling, every rank owns 10^6 (c2/c3) intervals
+    of a world*10^6-point mesh (configs[3] is c3 at 10^7 points over 8 GPUs).
+  * ``value``   : iterations/s with the state resident in HBM (CUDA events on the launching stream, max over ranks)
+  * ``e2e``     : the same through the host-buffer C-ABI calls a Rust host would make per iteration
+                  (rst_b200_set_state H2D -> rst_b200_newton_iterate -> rst_b200_get_state D2H)
+  * ``roofline``: dominant kernel, algorithmic bytes / measured launch duration vs
+                  MEASURED_PEAKS.json hbm_gbs
+  * ``cpu_baseline`` / ``--impl reference``: the CPU oracle (port of the reference's path; the Rust reference
+                  cannot be built in this image) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # key -> (problem, intervals per GPU, description)
+    "c1": ("linear2", 1_000, "2-variable BVP (examples/bvp_damped_aot_guide.rs), 1e3 mesh points"),
+    "c2": ("linear2", 1_000_000, "2-variable BVP (examples/bvp_damped_aot_guide.rs), 1e6 mesh points per GPU"),
+    "c3": ("flame12", 1_000_000, "12-variable flame BVP, 12x12 blocks, 1e6 mesh points per GPU"),
+}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons)}
+
+
+class RawCuda:
+    """Zero-copy view of a raw device pointer for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference's path, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    from rustedscithe_b200 import problems
+    key, n_local, desc = WORKLOADS[args.workload]
+    spec = problems.get(key)
+    # bounded sample: one damped Newton iteration (Jacobian + >= 2 refactor-per-solve linear solves,
+    # BVP_traits.rs:875-899) on a mesh capped so a step stays within tens of seconds
+    n = min(n_local, args.cpu_points)
+    o = orc.OracleBVP(key, n, spec.bc_list(), t0=spec.t0, t_end=spec.t_end)
+    lo, hi = spec.bounds_per_var()
+    lo, hi, rt = o.per_unknown(lo), o.per_unknown(hi), o.per_unknown(spec.rtol_per_var())
+    y0 = spec.guess(n)
+
+    def step():
+        t = time.perf_counter()
+        res = o.newton(y0, lo, hi, rt, abs_tol=spec.abs_tol, max_iterations=1, max_jac=spec.max_jac,
+                       max_damp_iter=spec.max_damp_iter, damp_factor=spec.damp_factor, refactor_per_solve=True)
+        return time.perf_counter() - t, res
+
+    for _ in range(args.warmup):
+        step()
+    times = [step()[0] for _ in range(args.steps)]
+    sec = float(np.mean(times))
+    # iterations/s on the sample, scaled to the full per-GPU mesh (cost is linear in N: banded LU O(n kl (kl+ku)))
+    value = (1.0 / sec) * (n / n_local)
+    line = {
+        "impl": "reference", "metric": "newton_iters_per_sec", "value": value, "unit": "iter/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * (n_local / n), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "problem": key, "points_per_gpu": n_local, "nv": spec.nv},
+        "cpu_baseline": {"value": value, "unit": "iter/s", "cores": orc.num_threads(), "kind": "port",
+                         "sample": f"one damped Newton iteration (Jacobian + refactor-per-solve banded LU) at {n} of "
+                                   f"{n_local} points, scaled linearly"},
+        "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--points", type=int, default=0, help="override intervals per GPU")
+    ap.add_argument("--cpu-points", type=int, default=1_000_000, help="mesh cap of the CPU sample")
+    ap.add_argument("--slab", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from rustedscithe_b200 import build as rbuild
+    from rustedscithe_b200 import lib as rlib
+    from rustedscithe_b200 import problems
+    from rustedscithe_b200.solver import NRBVP, DampedSolverOptions
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    if rank == 0 and not os.path.exists(rlib.LIB_PATH):
+        rbuild.build()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+
+    key, n_local, desc = WORKLOADS[args.workload]
+    if args.points:
+        n_local = args.points
+    spec = problems.get(key)
+    nv = spec.nv
+    n_global = n_local * world
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        opts = DampedSolverOptions.from_spec(spec, device=local_rank, stream=stream.cuda_stream, rank=rank,
+                                             world=world, slab=args.slab)
+        y0 = spec.guess(n_global)
+        solver = NRBVP(key, y0, n_global, opts)
+        if world > 1:
+            def allgather(send, recv, count, _stream):
+                s = torch.as_tensor(RawCuda(send, count), device="cuda")
+                r = torch.as_tensor(RawCuda(recv, count * world), device="cuda")
+                dist.all_gather_into_tensor(r, s)
+                return 0
+            solver.set_allgather(allgather)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def step():
+            st = solver.newton_iterate(recalc_jacobian=True)
+            if st < 0:
+                raise SystemExit(f"damped step failed with status {st}")
+
+        # ---- device-resident throughput -------------------------------------------------------------
+        for _ in range(args.warmup):
+            step()
+        launches0 = solver.launch_count()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = solver.launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        ms_per_step = ms / args.steps
+        # whole-job aggregate: Newton iterations/s normalised to the per-GPU mesh (weak scaling: an iteration of the
+        # world-times larger system counts as `world` unit iterations); equals plain iterations/s at N = 1
+        value = world * 1000.0 / ms_per_step
+
+        # ---- end to end through host buffers (what the Rust host does per iteration) ----------------------
+        host_y = torch.from_numpy(solver.get_state() if world == 1 else y0.copy()).pin_memory()
+        host_np = host_y.numpy()
+        Lc = solver.L
+        ptr = host_np.ctypes.data_as(C.POINTER(C.c_double))
+
+        def e2e_step():
+            rlib.check(Lc.rst_b200_set_state(solver.handle, ptr, host_np.shape[0]))
+            step()
+            rlib.check(Lc.rst_b200_get_state(solver.handle, ptr, host_np.shape[0]))
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record(stream)
+        barrier()
+        e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        bytes_local = (n_global if world == 1 else n_local) * nv * 8
+
+        # ---- per-phase kernel timings for the roofline (same stream, CUDA events, after warm-up) ----------
+        def time_phase(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        reps = max(5, min(50, args.steps))
+        phases = {}
+        if world == 1:
+            phases["assemble_FJ"] = time_phase(lambda: solver.eval_jacobian(0), reps)
+            phases["assemble_F"] = time_phase(lambda: solver.eval_residual(0), reps)
+            solver.eval_jacobian(0)
+            phases["factor"] = time_phase(lambda: solver.factor(), reps)
+            phases["solve"] = time_phase(lambda: solver.solve(), reps)
+        peak, peak_src = _peaks()
+        alg = {  # algorithmic bytes per interval, SURVEY.md section 8(d)
+            "assemble_FJ": 8 * (2 * nv + nv * nv), "assemble_F": 8 * 2 * nv,
+            "factor": 8 * 3 * nv * nv, "solve": 8 * (2 * nv * nv + 2 * nv),
+        }
+        roofline, kernels = None, {}
+        if phases:
+            for k, v in phases.items():
+                gbs = alg[k] * n_local / (v * 1e-3) / 1e9
+                kernels[k] = {"ms": v, "alg_bytes_per_interval": alg[k], "achieved_gbs": gbs, "frac": gbs / peak}
+            # per-iteration share: 1 FJ + 1 factor + 2 F + 2 solves (minimum iteration)
+            share = {"assemble_FJ": phases["assemble_FJ"], "factor": phases["factor"],
+                     "assemble_F": 2 * phases["assemble_F"], "solve": 2 * phases["solve"]}
+            dom = max(share, key=share.get)
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+                        "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                        "share_of_step": share[dom] / sum(share.values())}
+
+        # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the box's host cores -------------------
+        cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu:
+            from oracle import oracle as orc
+            n_cpu = min(n_local, args.cpu_points)
+            o = orc.OracleBVP(key, n_cpu, spec.bc_list(), t0=spec.t0, t_end=spec.t_end)
+            lo, hi = spec.bounds_per_var()
+            lo, hi, rt = o.per_unknown(lo), o.per_unknown(hi), o.per_unknown(spec.rtol_per_var())
+            tt = time.perf_counter()
+            reps_cpu = 0
+            while reps_cpu < 3 and time.perf_counter() - tt < 20.0:
+                res = o.newton(spec.guess(n_cpu), lo, hi, rt, abs_tol=spec.abs_tol, max_iterations=1,
+                               max_jac=spec.max_jac, max_damp_iter=spec.max_damp_iter, damp_factor=spec.damp_factor,
+                               refactor_per_solve=True)
+                reps_cpu += 1
+            sec = (time.perf_counter() - tt) / reps_cpu
+            cpu = {"value": (1.0 / sec) * (n_cpu / n_local), "unit": "iter/s", "cores": orc.num_threads(), "kind": "port",
+                   "sample": f"{reps_cpu} x one damped Newton iteration (Jacobian + {res.linear_solves} refactor-per-solve "
+                             f"banded LU solves) at {n_cpu} of {n_local} points, scaled linearly; assembly on all "
+                             f"threads, LU serial as in the reference"}
+
+        if rank == 0:
+            line = {
+                "metric": "newton_iters_per_sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps,
+                "unit_note": "Newton iterations per second per 1e6-point mesh slab, summed over GPUs (weak scaling)",
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {desc}", "problem": key, "nv": nv, "points_per_gpu": n_local,
+                           "points_total": n_global, "parallelism": f"mesh-slab x{world}",
+                           "l2_policy": "working set per step (state + blocks + factors) exceeds the 126 MB L2"
+                                        if n_local * nv * nv * 8 * 6 > 126e6 else "working set smaller than L2 (C1)",
+                           "step": "one damped Newton iteration incl. Jacobian refresh + factorisation"},
+                "clocks": clocks,
+                "e2e": {"value": world * 1000.0 / e2e_ms, "unit": "iter/s", "h2d_bytes_per_step": bytes_local,
+                        "d2h_bytes_per_step": bytes_local + 40 * max(1, solver.stats.linear_solves // max(1, solver.stats.iterations))},
+                "gpu_launches": int(launches),
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+                "newton": {"status": solver.stats.status, "linear_solves_per_iter":
+                           solver.stats.linear_solves / max(1, solver.stats.iterations)},
+            }
+            print(json.dumps(line), flush=True)
+        solver.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

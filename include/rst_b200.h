@@ -1,0 +1,188 @@
+/*
+ * rst_b200.h -- C ABI of the B200-native damped-Newton BVP hot path (librst_b200.so).
+ *
+ * Drop-in boundary for RustedSciThe's residual/Jacobian backend and banded-solver interfaces.
+ * Plain pointers and sizes only; every entry point returns an int status (never throws / panics
+ * across the ABI).  Paths below are relative to the reference repository root.
+ *
+ * Two groups of symbols:
+ *  (1) the reference's existing AOT artefact ABI, unchanged:
+ *        src/symbolic/codegen/c_backend/codegen_c_aot_library.rs:376-409 (exported C),
+ *        src/symbolic/codegen/codegen_aot_runtime_link.rs:38, :385-417 (dlopen side,
+ *        `unsafe extern "C" fn(*const f64, usize, *mut f64, usize) -> bool`)
+ *  (2) a device-resident handle API that the Rust-side `Fun` / `Jac` / `MatrixType` /
+ *      `DirectLinearSolver` shims call (src/numerical/BVP_Damp/BVP_traits.rs:459-461, :943-953,
+ *      :613-630; src/somelinalg/banded/solver_traits.rs:3-14), plus the whole damped loop
+ *      (src/numerical/BVP_Damp/NR_Damp_solver_damped.rs:1782-2156).
+ *
+ * A handle is thread-compatible (not thread-safe) and owns one CUDA stream's worth of work.
+ * There is no CPU fallback: without a CUDA device every call fails with RST_B200_ERR_CUDA.
+ */
+#ifndef RST_B200_H
+#define RST_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RST_B200_OK 0
+#define RST_B200_ERR_INVALID (-1)        /* bad argument / dimension mismatch (BandedError::DimensionMismatch, error.rs:4-39) */
+#define RST_B200_ERR_CUDA (-2)           /* CUDA runtime failure or no device */
+#define RST_B200_ERR_ZERO_PIVOT (-3)     /* BandedError::ZeroPivot */
+#define RST_B200_ERR_NAN (-4)            /* NaN in residual or step (panic in the reference, NR_Damp_solver_damped.rs:1821-1844) */
+#define RST_B200_ERR_UNSUPPORTED (-5)    /* problem key / block size not compiled in */
+#define RST_B200_ERR_NOT_FACTORIZED (-6) /* BandedError::NotFactorized */
+
+#define RST_B200_SCHEME_FORWARD 0
+#define RST_B200_SCHEME_TRAPEZOID 1
+
+typedef struct rst_b200_solver rst_b200_solver;
+
+/* Problem descriptor: the arguments of NRBVP::new_with_options (NR_Damp_solver_damped.rs:847) that
+ * the hot path needs, plus the mesh-slab partition for multi-GPU runs. */
+typedef struct {
+    const char *problem_key;   /* key of a compiled-in AOT problem (rst_b200_problem_key) */
+    int64_t n_steps;           /* GLOBAL number of intervals N (mesh has N+1 nodes, solver_common.rs:91-94) */
+    int scheme;                /* RST_B200_SCHEME_* (eq_step, symbolic_functions_BVP.rs:5221-5257) */
+    int trap_time;             /* trapezoid second-term time: 0 = t_j (symbolic route), 1 = t_{j+1} (closure route) */
+    double t0, t_end;          /* uniform mesh: h = (t_end - t0)/N, t_j = t0 + j*h (NR_Damp_solver_damped.rs:550-553) */
+    const double *mesh;        /* optional explicit GLOBAL mesh [N+1] (host); NULL = uniform */
+    int n_bc;                  /* must equal nv (numeric_discretization.rs:60-67) */
+    const int *bc_var;         /* variable index of each boundary condition */
+    const int *bc_side;        /* 0 = left (node 0), 1 = right (node N) */
+    const double *bc_val;
+    const double *params;      /* [n_params] (codegen_runtime_api.rs:74-83: args = [params..., unknowns...]) */
+    int n_params;
+    const double *lo, *hi;     /* per-variable bounds [nv] (looked up by base name, symbolic_functions_BVP.rs:5337-5378) */
+    const double *rtol;        /* per-variable relative tolerance [nv] */
+    int device;                /* CUDA device ordinal */
+    void *stream;              /* cudaStream_t to run on; NULL = the library creates its own */
+    int slab;                  /* rows per slab of the condensation (0 = library default) */
+    int rank, world;           /* mesh-slab partition: this process owns intervals [j_begin, j_end) of rank `rank` of `world` */
+} rst_b200_desc;
+
+typedef struct {
+    int max_iterations;        /* default 25 (NR_Damp_solver_damped.rs:444-459) */
+    int max_jac;               /* SolverParams.max_jac, default 3 (:142-151) */
+    int max_damp_iter;         /* default 5 */
+    double damp_factor;        /* default 0.5 */
+    double abs_tol;            /* default 1e-6 */
+} rst_b200_newton_opts;
+
+typedef struct {
+    int status;                /* 1 converged, 0 not converged, -2 no damping coefficient, -3 bound violation, RST_B200_ERR_* */
+    int iterations;            /* "number of iterations"                 (:2058-2061) */
+    int linear_solves;         /* "number of solving linear systems"     (:1881-1884) */
+    int jac_recalcs;           /* "number of jacobians recalculations"   (:1736-1738) */
+    int factorizations;        /* 1 per Jacobian here; the reference refactors per solve (BVP_traits.rs:875-899) */
+    double last_s0, last_s1, last_conv, last_fbound, last_lambda;
+    double ms_assemble, ms_factor, ms_solve, ms_total; /* CUDA-event timings, cumulative */
+} rst_b200_newton_stats;
+
+/* scalars of one damping trial, all that crosses PCIe inside the loop */
+typedef struct {
+    double sumsq_step;         /* ||step||_2^2 over unknowns */
+    double tol_sum;            /* sum |y_i| rtol_i over unknowns */
+    double fbound;             /* bound_step_Cantera2(y, step) */
+    double nan_flag;           /* != 0: NaN in F or step */
+    double device_flags;       /* RST_FLAG_* bits from the kernels (zero pivot) */
+} rst_b200_scalars;
+
+/* ---- library / problem registry ------------------------------------------------------------- */
+int rst_b200_version(void);
+int rst_b200_device_count(void);
+int rst_b200_problem_count(void);
+const char *rst_b200_problem_key(int index);
+/* nv, n_params, emitter hash (analogue of problem_key, codegen_aot_registry.rs) of a compiled-in problem */
+int rst_b200_problem_info(const char *key, int *nv, int *n_params, const char **hash);
+const char *rst_b200_last_error(void);
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+int rst_b200_create(const rst_b200_desc *desc, rst_b200_solver **out);
+void rst_b200_destroy(rst_b200_solver *s);
+int64_t rst_b200_n_unknowns(const rst_b200_solver *s);      /* local N_local * nv rows (global N*nv when world == 1) */
+int rst_b200_set_params(rst_b200_solver *s, const double *params, int n_params); /* re-bind parameters */
+int rst_b200_sync(rst_b200_solver *s);
+
+/* ---- state: reduced ordering (reference's unknown vector) <-> device-resident full state ---- */
+/* host y_reduced[N*nv] -> device (boundary slots pinned, numeric_discretization.rs:195-201) */
+int rst_b200_set_state(rst_b200_solver *s, const double *y_reduced, size_t len);
+int rst_b200_get_state(rst_b200_solver *s, double *y_reduced, size_t len);
+/* (N+1) x nv with boundary values re-inserted (construct_full_solution, BVP_utils.rs:534-558) */
+int rst_b200_get_full_solution(rst_b200_solver *s, double *full, size_t len);
+/* raw device pointers (double*): which = 0 Y, 1 F, 2 A, 3 B, 4 dY, 5 Y_trial, 6 interface rows, 7 interface rhs */
+void *rst_b200_device_ptr(rst_b200_solver *s, int which);
+
+/* ---- hot path, device resident ---------------------------------------------------------------- */
+/* F(Y) (Fun::call) ; which_state: 0 = current state, 1 = trial state */
+int rst_b200_eval_residual(rst_b200_solver *s, int which_state);
+/* F(Y) and the Jacobian blocks (Jac::call); invalidates the factorisation */
+int rst_b200_eval_jacobian(rst_b200_solver *s, int which_state);
+/* factor the current Jacobian blocks (LapackStyleBandedLuFaithful::factor_from replacement) */
+int rst_b200_factor(rst_b200_solver *s);
+/* dY = J^{-1} F (MatrixType::solve_sys on the cached factors) */
+int rst_b200_solve(rst_b200_solver *s);
+/* reductions of the current step against state `which_state` */
+int rst_b200_reduce(rst_b200_solver *s, int which_state, rst_b200_scalars *out);
+/* Y_trial = Y - lambda dY */
+int rst_b200_make_trial(rst_b200_solver *s, double lambda);
+/* accept the trial state as the current state */
+int rst_b200_accept_trial(rst_b200_solver *s);
+
+/* whole damped Newton loop (try_main_loop_damped, NR_Damp_solver_damped.rs:2027-2156) */
+int rst_b200_newton_solve(rst_b200_solver *s, const rst_b200_newton_opts *opts, rst_b200_newton_stats *stats);
+/* ONE iteration of that loop from the current state (bench step): recalc_jacobian != 0 forces a
+ * Jacobian evaluation + factorisation first. Returns the damped_step status (1 / 0 / -2 / -3). */
+int rst_b200_newton_iterate(rst_b200_solver *s, const rst_b200_newton_opts *opts, int recalc_jacobian,
+                            rst_b200_newton_stats *stats);
+
+/* ---- host-pointer drop-ins ---------------------------------------------------------------------- */
+/* DirectLinearSolver::solve_in_place (solver_traits.rs:3-14): rhs[N*nv] in the reference's row order,
+ * overwritten with the solution in the reference's reduced column order. Needs rst_b200_factor. */
+int rst_b200_solve_in_place(rst_b200_solver *s, double *rhs, size_t len);
+/* solve_multiple_in_place: column-major, leading dimension ldb >= n */
+int rst_b200_solve_multiple_in_place(rst_b200_solver *s, double *rhs, size_t nrhs, size_t ldb);
+/* sparse/banded structure of the value stream (BandedJacobianStructure, codegen_runtime_api.rs:414-421):
+ * returns nnz; arrays may be NULL */
+int64_t rst_b200_jacobian_structure(rst_b200_solver *s, int64_t *rows, int64_t *cols, int64_t *diag_offsets,
+                                    int64_t *diag_positions, int *kl, int *ku);
+
+/* ---- the reference's AOT artefact ABI (codegen_c_aot_library.rs:376-409), bound to one handle ---- */
+/* args = [params..., y_reduced...]; returns 1 ok / 0 on NULL pointer or length mismatch (:382-384) */
+int rst_b200_aot_bind(rst_b200_solver *s);
+int rustedscithe_aot_eval_residual(const double *args, size_t args_len, double *out, size_t out_len);
+int rustedscithe_aot_eval_jacobian_values(const double *args, size_t args_len, double *out, size_t out_len);
+
+/* ---- multi-GPU mesh slabs -------------------------------------------------
+ * Each rank owns a contiguous slab of intervals and condenses it to ONE interface block row
+ * (2 nv^2 + nv doubles); the `world` interface rows form a tiny block-bidiagonal system that every
+ * rank solves redundantly.  The only data-path exchange is an all-gather of those rows; the library
+ * calls back into the host application for it (torch.distributed / NCCL over NVLink). */
+typedef int (*rst_b200_allgather_fn)(void *ctx, const void *d_send, void *d_recv, int64_t doubles_per_rank,
+                                     void *stream);
+int rst_b200_set_allgather(rst_b200_solver *s, rst_b200_allgather_fn fn, void *ctx);
+/* local intervals [begin, end) of this rank */
+int rst_b200_dist_range(const rst_b200_solver *s, int64_t *j_begin, int64_t *j_end);
+/* phase-split primitives (rst_b200_factor / _solve / _reduce call them around the all-gather callback;
+ * exposed so a single process can drive several emulated ranks):
+ *   buffers: which = 6 interface rows [2 nv^2] (send), 7 interface rhs [nv] (send), 8 gathered rows
+ *   [world][2 nv^2] (recv), 9 gathered rhs [world][nv] (recv), 10 scalars [8] (send), 11 gathered scalars */
+int rst_b200_factor_local(rst_b200_solver *s);
+int rst_b200_factor_reduced(rst_b200_solver *s);
+int rst_b200_solve_local_forward(rst_b200_solver *s);
+int rst_b200_solve_reduced_backward(rst_b200_solver *s);
+int rst_b200_reduce_local(rst_b200_solver *s, int which_state);
+int rst_b200_reduce_finish(rst_b200_solver *s, rst_b200_scalars *out);
+
+/* synchronous cudaMemcpy on raw pointers (kind: 1 H2D, 2 D2H, 3 D2D) -- lets a host language without CUDA
+ * bindings move data to / from rst_b200_device_ptr buffers */
+int rst_b200_memcpy(void *dst, const void *src, size_t bytes, int kind);
+
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t rst_b200_launch_count(const rst_b200_solver *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

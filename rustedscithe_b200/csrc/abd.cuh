@@ -1,0 +1,372 @@
+// abd.cuh -- pivoted recursive condensation solver for the block-bidiagonal ("almost block diagonal")
+// Newton systems of the discretised BVP (north_star subsystem 2).
+//
+// Replaces, on the GPU, the reference's serial scalar banded LU
+//   src/somelinalg/banded/lapack_style_banded.rs:386-475 (factor), :1163-1225 (solve)
+// and its block-tridiagonal LU (block_tridiagonal_lu_consistent.rs:98-218).  The linear system is
+//   A_j dY_j + B_j dY_{j+1} = r_j ,  j = 0..n-1   (A_j = -I - h f_y, B_j = I for the forward scheme,
+//   src/numerical/BVP_Damp/numeric_discretization.rs:328-342) plus nv pinned boundary components.
+// Diagonal blocks of the reduced-ordering matrix are structurally singular,
+// so every elimination uses row partial pivoting across the two block rows that share a node:
+//
+//   slab of S consecutive block rows -> march through the slab; at each step the shared node Y_j of the
+//   running condensed row [C | D] (couples slab-start node Y_s and Y_j) and the next row [A_j | B_j] is
+//   eliminated by LU with partial pivoting on the stacked 2nv x nv column [D; A_j].  The nv pivot rows
+//   are kept for back-substitution (U Y_j = e - E Y_s - F Y_{j+1}), the nv surviving rows become the new
+//   condensed row.  Each slab ends as ONE block row coupling its two end nodes -> a block-bidiagonal
+//   system S times smaller -> recurse (levels) until one row is left, which is closed with the boundary
+//   conditions (abd_top_solve_kernel).  Factor and solve are separate so the damped loop re-uses factors.
+//
+// Thread mapping ("lanes per slab"): one lane per row of the stacked 2nv-row panel, G = pow2 >= 2nv
+// lanes per slab (nv <= 16), 32/G slabs per warp; a lane keeps its row [M | P | Q] (coefficients of the
+// node being eliminated, of the slab-start node, of the next node) in registers; pivot search is a
+// warp-shuffle arg-max, the pivot row is broadcast with shuffles.  Rows never move between lanes: the
+// nv surviving lanes carry the condensed row, the nv pivot lanes are re-used to load the next block row.
+//
+// HBM layout of the factors (per eliminated node g, lane-fastest so every access is coalesced):
+//   Lm [g][k][r]   k < nv, r < 2nv : multiplier of row r at elimination step k (valid while unpivoted)
+//   UEF[g][c][k]   c < 3nv, k < nv : pivot row k: U (c < nv, valid for c >= k) | E (Y_s coeffs) | F (Y_{j+1} coeffs)
+//   piv[g][r]      int8           : elimination step at which row r became the pivot row, -1 = survivor
+#pragma once
+#include "rst_common.cuh"
+
+namespace rst {
+
+struct AbdLevel {
+    int64_t n;         // block rows at this level
+    int64_t nslabs;    // ceil(n / S) = block rows of the next level
+    int S;             // slab length (rows per slab)
+    const double *A;   // [n][nv][nv] row-major
+    const double *B;   // [n][nv][nv] or nullptr (identity)
+    double *A_next;    // [nslabs][nv][nv]
+    double *B_next;    // [nslabs][nv][nv]
+    double *Lm;        // [n][nv][2nv]
+    double *UEF;       // [n][3nv][nv]
+    int8_t *piv;       // [n][2nv]
+    const double *r;   // [n][nv]      right-hand side of this level
+    double *e;         // [n][nv]      transformed rhs of the pivot rows
+    double *r_next;    // [nslabs][nv]
+    double *Z;         // [n+1][nv]    node values of this level (level 0: dY)
+    const double *Z_next;  // [nslabs+1][nv]
+};
+
+// rank of this lane among the set bits of `bits` restricted to its group (bits already shifted to the group)
+__device__ __forceinline__ int rank_in(unsigned gbits, int r) { return __popc(gbits & ((1u << r) - 1u)); }
+
+template <int G>
+__device__ __forceinline__ unsigned group_bits(unsigned ballot, int gw) {
+    if (G == 32) return ballot;
+    return (ballot >> (gw * G)) & ((1u << G) - 1u);
+}
+
+// arg-max of |v| over the lanes of a group that are still candidates; returns the group-relative lane.
+// Key = bits(|v|) with the low 5 mantissa bits replaced by (31 - r): ties resolve to the lowest row,
+// the comparison ignores the last 5 of 52 mantissa bits (irrelevant for stability).
+template <int G>
+__device__ __forceinline__ int group_argmax(double v, bool cand, int r) {
+    long long key = cand ? ((__double_as_longlong(fabs(v)) & ~31LL) | (long long)(31 - r)) : -1LL;
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) {
+        const long long o = __shfl_xor_sync(RST_FULL_MASK, key, off);
+        key = o > key ? o : key;
+    }
+    return 31 - (int)(key & 31LL);
+}
+
+// ------------------------------------------------------------------------------------------------
+// factor: one level of condensation
+// ------------------------------------------------------------------------------------------------
+template <int NV, bool IDENT_B>
+__global__ void __launch_bounds__(128) abd_factor_kernel(AbdLevel L, unsigned *flags) {
+    constexpr int R2 = 2 * NV;
+    constexpr int G = next_pow2(R2);
+    static_assert(G <= 32, "lanes-per-slab kernel supports nv <= 16");
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int r = lane & (G - 1);
+    const int gw = lane / G;
+    const int64_t slab = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + gw;
+    const bool slab_ok = slab < L.nslabs;
+    const bool row_ok = r < R2;
+    const int64_t g0 = slab * (int64_t)L.S;
+    const int len = slab_ok ? (int)((L.n - g0) < (int64_t)L.S ? (L.n - g0) : (int64_t)L.S) : 0;
+
+    double M[NV], P[NV], Q[NV];
+    bool carry = slab_ok && r < NV;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) { M[c] = 0.0; P[c] = 0.0; Q[c] = 0.0; }
+    if (carry) {
+        const double *a = L.A + (g0 * NV + r) * NV;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) P[c] = a[c];
+        if (IDENT_B) {
+#pragma unroll
+            for (int c = 0; c < NV; ++c) M[c] = (c == r) ? 1.0 : 0.0;
+        } else {
+            const double *b = L.B + (g0 * NV + r) * NV;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) M[c] = b[c];
+        }
+    }
+
+    for (int i = 1; i < L.S; ++i) {
+        const bool active = i < len;  // uniform per group; every lane still joins the shuffles
+        const int64_t g = g0 + i;
+        const bool is_free = row_ok && !carry;
+        const unsigned fb = group_bits<G>(__ballot_sync(RST_FULL_MASK, is_free), gw);
+        if (active && is_free) {
+            const int t = rank_in(fb, r);
+            const double *a = L.A + (g * NV + t) * NV;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) { M[c] = a[c]; P[c] = 0.0; }
+            if (IDENT_B) {
+#pragma unroll
+                for (int c = 0; c < NV; ++c) Q[c] = (c == t) ? 1.0 : 0.0;
+            } else {
+                const double *b = L.B + (g * NV + t) * NV;
+#pragma unroll
+                for (int c = 0; c < NV; ++c) Q[c] = b[c];
+            }
+        }
+        int pv = -1;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const bool cand = active && row_ok && pv < 0;
+            const int p = group_argmax<G>(M[k], cand, r);
+            const double pivval = shfl_d(M[k], p, G);
+            const bool is_piv = cand && (r == p);
+            if (is_piv) {
+                pv = k;
+                if (!(fabs(pivval) > 0.0)) atomicOr(flags, RST_FLAG_ZERO_PIVOT);
+            }
+            const bool upd = cand && !is_piv;
+            const double l = upd ? M[k] / pivval : 0.0;
+            if (upd) M[k] = l;
+#pragma unroll
+            for (int c = k + 1; c < NV; ++c) {
+                const double mp = shfl_d(M[c], p, G);
+                M[c] = fma(-l, mp, M[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                const double pp = shfl_d(P[c], p, G);
+                P[c] = fma(-l, pp, P[c]);
+                const double qp = shfl_d(Q[c], p, G);
+                Q[c] = fma(-l, qp, Q[c]);
+            }
+        }
+        if (active) {
+            if (row_ok) {
+                double *lm = L.Lm + g * (int64_t)(NV * R2) + r;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) st_cs(lm + k * R2, M[k]);
+                L.piv[g * R2 + r] = (int8_t)pv;
+                if (pv >= 0) {
+                    double *u = L.UEF + g * (int64_t)(3 * NV * NV) + pv;
+#pragma unroll
+                    for (int c = 0; c < NV; ++c) {
+                        st_cs(u + c * NV, M[c]);
+                        st_cs(u + (NV + c) * NV, P[c]);
+                        st_cs(u + (2 * NV + c) * NV, Q[c]);
+                    }
+                }
+            }
+            carry = row_ok && pv < 0;
+            if (carry) {
+#pragma unroll
+                for (int c = 0; c < NV; ++c) { M[c] = Q[c]; Q[c] = 0.0; }
+            }
+        }
+    }
+    const unsigned cb = group_bits<G>(__ballot_sync(RST_FULL_MASK, carry), gw);
+    if (slab_ok && carry) {
+        const int t = rank_in(cb, r);
+        double *a = L.A_next + (slab * NV + t) * NV;
+        double *b = L.B_next + (slab * NV + t) * NV;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) { a[c] = P[c]; b[c] = M[c]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// solve, forward sweep of one level: apply the recorded eliminations to the right-hand side
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(128) abd_forward_kernel(AbdLevel L) {
+    constexpr int R2 = 2 * NV;
+    constexpr int G = next_pow2(R2);
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int r = lane & (G - 1);
+    const int gw = lane / G;
+    const int64_t slab = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + gw;
+    const bool slab_ok = slab < L.nslabs;
+    const bool row_ok = r < R2;
+    const int64_t g0 = slab * (int64_t)L.S;
+    const int len = slab_ok ? (int)((L.n - g0) < (int64_t)L.S ? (L.n - g0) : (int64_t)L.S) : 0;
+
+    bool carry = slab_ok && r < NV;
+    double w = carry ? L.r[g0 * NV + r] : 0.0;
+
+    for (int i = 1; i < L.S; ++i) {
+        const bool active = i < len;
+        const int64_t g = g0 + i;
+        const bool is_free = row_ok && !carry;
+        const unsigned fb = group_bits<G>(__ballot_sync(RST_FULL_MASK, is_free), gw);
+        int pv = -1;
+        double lrow[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) lrow[k] = 0.0;
+        if (active && row_ok) {
+            if (is_free) w = L.r[g * NV + rank_in(fb, r)];
+            pv = (int)L.piv[g * R2 + r];
+            const double *lm = L.Lm + g * (int64_t)(NV * R2) + r;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) lrow[k] = ld_cs(lm + k * R2);
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const unsigned pb = group_bits<G>(__ballot_sync(RST_FULL_MASK, pv == k), gw);
+            const int p = pb ? (__ffs(pb) - 1) : 0;
+            const double wp = shfl_d(w, p, G);
+            if (pv < 0 || pv > k) w = fma(-lrow[k], wp, w);
+        }
+        if (active && row_ok) {
+            if (pv >= 0) L.e[g * NV + pv] = w;
+            carry = pv < 0;
+        }
+    }
+    const unsigned cb = group_bits<G>(__ballot_sync(RST_FULL_MASK, carry), gw);
+    if (slab_ok && carry) L.r_next[slab * NV + rank_in(cb, r)] = w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// solve, backward sweep of one level: recover the interior nodes of every slab from its end nodes
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(128) abd_backward_kernel(AbdLevel L) {
+    constexpr int G = next_pow2(NV);
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int k = lane & (G - 1);
+    const int gw = lane / G;
+    const int64_t slab = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + gw;
+    const bool slab_ok = slab < L.nslabs;
+    const bool k_ok = slab_ok && k < NV;
+    const int64_t g0 = slab * (int64_t)L.S;
+    const int len = slab_ok ? (int)((L.n - g0) < (int64_t)L.S ? (L.n - g0) : (int64_t)L.S) : 0;
+
+    double Ys[NV], Yn[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+        Ys[c] = slab_ok ? L.Z_next[slab * NV + c] : 0.0;
+        Yn[c] = slab_ok ? L.Z_next[(slab + 1) * NV + c] : 0.0;
+    }
+    if (k_ok) {
+        double ys = 0.0, yn = 0.0;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) { ys = (c == k) ? Ys[c] : ys; yn = (c == k) ? Yn[c] : yn; }
+        L.Z[g0 * NV + k] = ys;
+        if (slab == L.nslabs - 1) L.Z[L.n * NV + k] = yn;
+    }
+    for (int i = L.S - 1; i >= 1; --i) {
+        const bool active = i < len;
+        const int64_t g = g0 + i;
+        double U[NV];
+        double t = 0.0, inv = 1.0;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) U[c] = 0.0;
+        if (active && k_ok) {
+            const double *u = L.UEF + g * (int64_t)(3 * NV * NV) + k;
+            t = L.e[g * NV + k];
+            double diag = 1.0;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                U[c] = ld_cs(u + c * NV);
+                t = fma(-ld_cs(u + (NV + c) * NV), Ys[c], t);
+                t = fma(-ld_cs(u + (2 * NV + c) * NV), Yn[c], t);
+                diag = (c == k) ? U[c] : diag;
+            }
+            inv = 1.0 / diag;
+        }
+#pragma unroll
+        for (int kk = NV - 1; kk >= 0; --kk) {
+            const double y = shfl_d(t * inv, kk, G);
+            if (k < kk) t = fma(-U[kk], y, t);
+            if (active) Yn[kk] = y;
+        }
+        if (active && k_ok) {
+            double mine = 0.0;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) mine = (c == k) ? Yn[c] : mine;
+            L.Z[g * NV + k] = mine;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// top of the recursion: the single remaining block row  C Z0 + D Z1 = g  closed with the boundary
+// conditions (pinned components have zero correction): an nv x nv dense system in the free components
+// of Z0 and Z1 (numeric_discretization.rs:80-106 deletes exactly those columns), solved by one warp
+// with partial pivoting in shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(32) abd_top_solve_kernel(const double *C, const double *D, const double *g,
+                                                           double *Z /* [2][nv] */, unsigned long long left_mask,
+                                                           unsigned long long right_mask, unsigned *flags) {
+    __shared__ double K[NV][NV + 1];
+    __shared__ int colmap[NV];
+    const int lane = threadIdx.x;
+    if (lane == 0) {
+        int nc = 0;
+        for (int c = 0; c < NV; ++c)
+            if (!((left_mask >> c) & 1ull)) colmap[nc++] = c;
+        for (int c = 0; c < NV; ++c)
+            if (!((right_mask >> c) & 1ull)) { if (nc < NV) colmap[nc] = NV + c; ++nc; }
+        if (nc != NV) atomicOr(flags, RST_FLAG_ZERO_PIVOT);
+    }
+    __syncwarp();
+    for (int idx = lane; idx < NV * NV; idx += 32) {
+        const int row = idx / NV, cc = idx % NV;
+        const int cm = colmap[cc];
+        K[row][cc] = cm < NV ? C[row * NV + cm] : D[row * NV + (cm - NV)];
+    }
+    for (int row = lane; row < NV; row += 32) K[row][NV] = g[row];
+    __syncwarp();
+    for (int k = 0; k < NV; ++k) {
+        // pivot search (lane-strided rows), then swap rows k <-> p
+        double best = -1.0;
+        int bi = k;
+        for (int row = k + lane; row < NV; row += 32) {
+            const double v = fabs(K[row][k]);
+            if (v > best) { best = v; bi = row; }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const double ob = __shfl_xor_sync(RST_FULL_MASK, best, off);
+            const int oi = __shfl_xor_sync(RST_FULL_MASK, bi, off);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (!(best > 0.0)) { if (lane == 0) atomicOr(flags, RST_FLAG_ZERO_PIVOT); }
+        if (bi != k)
+            for (int c = lane; c <= NV; c += 32) { const double tmp = K[k][c]; K[k][c] = K[bi][c]; K[bi][c] = tmp; }
+        __syncwarp();
+        const double pivval = K[k][k];
+        for (int row = k + 1 + lane; row < NV; row += 32) {
+            const double l = K[row][k] / pivval;
+            for (int c = k + 1; c <= NV; ++c) K[row][c] = fma(-l, K[k][c], K[row][c]);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        for (int row = NV - 1; row >= 0; --row) {
+            double s = K[row][NV];
+            for (int c = row + 1; c < NV; ++c) s = fma(-K[row][c], K[c][NV], s);
+            K[row][NV] = s / K[row][row];
+        }
+        for (int c = 0; c < 2 * NV; ++c) Z[c] = 0.0;
+        for (int cc = 0; cc < NV; ++cc) Z[colmap[cc]] = K[cc][NV];
+    }
+}
+
+}  // namespace rst

@@ -1,0 +1,119 @@
+// assemble.cuh -- fused residual + Jacobian-block assembly over all mesh intervals (north_star
+// subsystem 1).  One thread owns one interval j; the per-point mathematics comes from the struct the
+// CUDA-C emitter generated (rustedscithe_b200/emit/cuda_emitter.py), the discretisation is restated
+// from the reference:
+//   forward    r[j,i] = Y[j+1][i] - Y[j][i] - h_j f_i(t_j, Y[j])
+//              (src/symbolic/symbolic_functions_BVP.rs:5486-5490, numeric_discretization.rs:236)
+//              A_j = dr_j/dY_j = -I - h_j f_y(t_j, Y_j),  B_j = dr_j/dY_{j+1} = +I   (:329-341)
+//   trapezoid  r = Y[j+1] - Y[j] - h/2 (f(t_j,Y_j) + f(t*,Y_{j+1})), t* = t_j on the symbolic route
+//              (symbolic_functions_BVP.rs:5250-5253), t_{j+1} on the closure route
+//              (numeric_discretization.rs:223-232);  A_j = -I - h/2 f_y(Y_j), B_j = +I - h/2 f_y(Y_{j+1})
+// State is the FULL (N+1) x nv node-major array with boundary slots pinned (SURVEY.md hard part 2),
+// J is written directly in the block layout the solver consumes: A[j][nv][nv] row-major (B implicit
+// identity for the forward scheme).
+#pragma once
+#include "rst_common.cuh"
+
+namespace rst {
+
+struct AsmArgs {
+    const double *Y;       // [(n+1)][nv]
+    double *F;             // [n][nv]
+    double *A;             // [n][nv][nv]   (nullptr when only F is wanted)
+    double *B;             // [n][nv][nv]   trapezoid only
+    const double *mesh;    // [n+1] or nullptr for a uniform mesh
+    const double *params;  // [np] device
+    double t0, h;          // uniform mesh: t_j = t0 + (j + j_offset) * h  (multiplication, :5307)
+    int64_t n;             // local intervals
+    int64_t j_offset;      // global index of local interval 0 (mesh slabs across GPUs)
+    int trap_time;         // trapezoid second-term time: 0 = t_j, 1 = t_{j+1}
+};
+
+template <int NV>
+__device__ __forceinline__ void load_node(const double *src, double *dst) {
+    if constexpr (NV % 2 == 0) {
+        const double2 *s2 = reinterpret_cast<const double2 *>(src);
+#pragma unroll
+        for (int c = 0; c < NV / 2; ++c) {
+            const double2 v = s2[c];
+            dst[2 * c] = v.x;
+            dst[2 * c + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < NV; ++c) dst[c] = src[c];
+    }
+}
+
+// block = identity_sign * I - hs * fy, streamed out (written once, read once by the factor kernel)
+template <int NV>
+__device__ __forceinline__ void store_block(double *dst, const double *fy, double hs, double idsign) {
+    if constexpr ((NV * NV) % 2 == 0) {
+        double2 *d2 = reinterpret_cast<double2 *>(dst);
+#pragma unroll
+        for (int e = 0; e < NV * NV / 2; ++e) {
+            const int i0 = (2 * e) / NV, c0 = (2 * e) % NV, i1 = (2 * e + 1) / NV, c1 = (2 * e + 1) % NV;
+            double2 v;
+            v.x = fma(-hs, fy[2 * e], (i0 == c0) ? idsign : 0.0);
+            v.y = fma(-hs, fy[2 * e + 1], (i1 == c1) ? idsign : 0.0);
+            st_cs2(d2 + e, v);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < NV * NV; ++e) st_cs(dst + e, fma(-hs, fy[e], ((e / NV) == (e % NV)) ? idsign : 0.0));
+    }
+}
+
+template <class P, bool WITH_J, bool TRAPEZOID>
+__global__ void __launch_bounds__(128) assemble_kernel(AsmArgs a) {
+    constexpr int NV = P::NV;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.n) return;
+    double y0[NV], y1[NV], f0[NV];
+    load_node<NV>(a.Y + j * NV, y0);
+    load_node<NV>(a.Y + (j + 1) * NV, y1);
+    double t, t1, h;
+    if (a.mesh) {
+        t = a.mesh[j];
+        t1 = a.mesh[j + 1];
+        h = t1 - t;
+    } else {
+        t = a.t0 + (double)(j + a.j_offset) * a.h;
+        t1 = a.t0 + (double)(j + a.j_offset + 1) * a.h;
+        h = a.h;
+    }
+    double *r = a.F + j * NV;
+    if constexpr (!TRAPEZOID) {
+        if constexpr (WITH_J) {
+            double fy[NV * NV];
+            P::eval_f_fy(t, y0, a.params, f0, fy);
+            store_block<NV>(a.A + j * (int64_t)(NV * NV), fy, h, -1.0);
+        } else {
+            P::eval_f(t, y0, a.params, f0);
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) r[i] = y1[i] - y0[i] - h * f0[i];
+    } else {
+        double f1[NV];
+        const double tt = a.trap_time ? t1 : t;
+        if constexpr (WITH_J) {
+            {
+                double fy[NV * NV];
+                P::eval_f_fy(t, y0, a.params, f0, fy);
+                store_block<NV>(a.A + j * (int64_t)(NV * NV), fy, 0.5 * h, -1.0);
+            }
+            {
+                double fy[NV * NV];
+                P::eval_f_fy(tt, y1, a.params, f1, fy);
+                store_block<NV>(a.B + j * (int64_t)(NV * NV), fy, 0.5 * h, 1.0);
+            }
+        } else {
+            P::eval_f(t, y0, a.params, f0);
+            P::eval_f(tt, y1, a.params, f1);
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) r[i] = y1[i] - y0[i] - 0.5 * h * (f0[i] + f1[i]);
+    }
+}
+
+}  // namespace rst

@@ -1,0 +1,191 @@
+// newton.cuh -- device-resident pieces of the damped Newton driver (north_star subsystem 3): the
+// state, residual, Jacobian blocks, factors and steps stay in HBM; only a handful of scalars per
+// damping trial cross PCIe.
+//
+// Reference semantics restated here (src/numerical/BVP_Damp/):
+//   y_trial = y - lambda * step                      NR_Damp_solver_damped.rs:1934-1935
+//   s       = ||step||_2                             :1924, :1947 (nalgebra norm, BVP_traits.rs:283)
+//   conv    = max(sum_i |y_i| rtol_i, atol)          BVP_utils_damped.rs:209-222 (unknowns only)
+//   fbound  = bound_step_Cantera2(y, step, bounds)   BVP_utils_damped.rs:39-61 (evaluates y + step)
+//   NaN scans of F and of the step                   NR_Damp_solver_damped.rs:1821-1826, :1839-1844
+// The full (N+1) x nv node-major state keeps boundary slots pinned; `left_mask` / `right_mask` mark the
+// pinned components of node 0 / node N so reductions run over the reference's unknowns only.
+#pragma once
+#include "rst_common.cuh"
+
+namespace rst {
+
+struct ReduceArgs {
+    const double *Y;      // state the tolerance sum / bound guard refer to   [(n+1)*nv]
+    const double *dY;     // step                                             [(n+1)*nv]
+    const double *F;      // residual (NaN scan only, may be nullptr)          [n*nv]
+    const double *lo, *hi, *rtol;  // per variable [nv]
+    int64_t n_nodes;      // nodes this rank owns
+    int64_t n_rows;       // residual block rows this rank owns (NaN scan of F)
+    int nv;
+    unsigned long long left_mask, right_mask;
+    int has_left, has_right;  // this rank owns global node 0 / global node N
+    double *partials;     // [gridDim.x][4]: sumsq(step), sum |y| rtol, min fbound, nan flags
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(RST_FULL_MASK, v, off);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = fmin(v, __shfl_xor_sync(RST_FULL_MASK, v, off));
+    return v;
+}
+
+// one pass over the step: all scalars a damping trial needs
+__global__ void __launch_bounds__(256) newton_reduce_kernel(ReduceArgs a) {
+    const int64_t total = a.n_nodes * a.nv;
+    double ss = 0.0, tol = 0.0, fb = 1.0, nanf = 0.0;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t node = idx / a.nv;
+        const int v = (int)(idx - node * a.nv);
+        const bool pinned = (a.has_left && node == 0 && ((a.left_mask >> v) & 1ull)) ||
+                            (a.has_right && node == a.n_nodes - 1 && ((a.right_mask >> v) & 1ull));
+        const double s = a.dY[idx];
+        if (s != s) nanf = 2.0;
+        if (pinned) continue;
+        const double y = a.Y[idx];
+        ss = fma(s, s, ss);
+        tol = fma(fabs(y), a.rtol[v], tol);
+        const double nv_ = y + s;  // the reference evaluates y + step although it applies y - lambda*step
+        if (nv_ > a.hi[v]) fb = fmax(fmin(fb, (a.hi[v] - y) / (nv_ - y)), 0.0);
+        else if (nv_ < a.lo[v]) fb = fmin(fb, (y - a.lo[v]) / (y - nv_));
+    }
+    if (a.F) {
+        const int64_t nf = a.n_rows * a.nv;
+        for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nf;
+             idx += (int64_t)gridDim.x * blockDim.x) {
+            const double f = a.F[idx];
+            if (f != f) nanf = fmax(nanf, 1.0);
+        }
+    }
+    __shared__ double sh[4][8];
+    ss = warp_sum(ss);
+    tol = warp_sum(tol);
+    fb = warp_min(fb);
+    nanf = -warp_min(-nanf);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = ss; sh[1][w] = tol; sh[2][w] = fb; sh[3][w] = nanf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a0 = 0.0, a1 = 0.0, a2 = 1.0, a3 = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+            a0 += sh[0][i]; a1 += sh[1][i]; a2 = fmin(a2, sh[2][i]); a3 = fmax(a3, sh[3][i]);
+        }
+        double *p = a.partials + 4 * (int64_t)blockIdx.x;
+        p[0] = a0; p[1] = a1; p[2] = a2; p[3] = a3;
+    }
+}
+
+// deterministic second stage: out[0..3] = {sumsq, tolsum, fbound, nanflag}; out[4] = device error flags
+__global__ void __launch_bounds__(256) newton_reduce_final_kernel(const double *partials, int nblocks, double *out,
+                                                                  const unsigned *flags) {
+    double a0 = 0.0, a1 = 0.0, a2 = 1.0, a3 = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
+        a0 += partials[4 * i]; a1 += partials[4 * i + 1];
+        a2 = fmin(a2, partials[4 * i + 2]); a3 = fmax(a3, partials[4 * i + 3]);
+    }
+    __shared__ double sh[4][8];
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_min(a2); a3 = -warp_min(-a3);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = a0; sh[1][w] = a1; sh[2][w] = a2; sh[3][w] = a3; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b0 = 0.0, b1 = 0.0, b2 = 1.0, b3 = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+            b0 += sh[0][i]; b1 += sh[1][i]; b2 = fmin(b2, sh[2][i]); b3 = fmax(b3, sh[3][i]);
+        }
+        out[0] = b0; out[1] = b1; out[2] = b2; out[3] = b3;
+        out[4] = (double)(*flags);
+    }
+}
+
+// y_trial = y - lambda * step   (NR_Damp_solver_damped.rs:1934-1935: mul_float, then subtraction)
+__global__ void __launch_bounds__(256) newton_trial_kernel(const double *__restrict__ Y, const double *__restrict__ dY,
+                                                           double *__restrict__ Yt, double lambda, int64_t total) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x)
+        Yt[idx] = Y[idx] - dY[idx] * lambda;
+}
+
+// ---- reduced ordering <-> full node-major state (numeric_discretization.rs:80-106, BVP_utils.rs:534-558) ----
+// reduced index k -> full position: the nl pinned slots of node 0 and the nr pinned slots of node N are deleted
+struct LayoutArgs {
+    int64_t n_steps;
+    int nv;
+    int nl, nr;
+    int left_free[64];   // free components of node 0, ascending
+    int right_free[64];  // free components of node N, ascending
+};
+
+__device__ __forceinline__ int64_t reduced_to_full(const LayoutArgs &a, int64_t k) {
+    const int64_t first = a.nv - a.nl;
+    if (k < first) return a.left_free[k];
+    const int64_t interior_end = first + (a.n_steps - 1) * (int64_t)a.nv;
+    if (k < interior_end) return k + a.nl;
+    return a.n_steps * (int64_t)a.nv + a.right_free[k - interior_end];
+}
+
+__global__ void __launch_bounds__(256) scatter_reduced_kernel(LayoutArgs a, const double *__restrict__ reduced,
+                                                              double *__restrict__ full) {
+    const int64_t n = a.n_steps * (int64_t)a.nv;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        full[reduced_to_full(a, k)] = reduced[k];
+}
+__global__ void __launch_bounds__(256) gather_reduced_kernel(LayoutArgs a, const double *__restrict__ full,
+                                                             double *__restrict__ reduced) {
+    const int64_t n = a.n_steps * (int64_t)a.nv;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        reduced[k] = full[reduced_to_full(a, k)];
+}
+
+// Jacobian value stream in the reference's entry order (sorted (row, col), symbolic_functions_BVP.rs:1343):
+// src[k] >= 0: element offset into A; -1: the +1 identity entry of B (forward); <= -2: offset -(src+2) into B
+__global__ void __launch_bounds__(256) gather_values_kernel(const int64_t *__restrict__ src, const double *__restrict__ A,
+                                                            const double *__restrict__ B, double *__restrict__ out,
+                                                            int64_t nnz) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = src[k];
+        out[k] = s >= 0 ? A[s] : (s == -1 ? 1.0 : B[-(s + 2)]);
+    }
+}
+
+// residual check r = rhs - J x in block form (used by the guarded refinement, lapack_style_banded.rs:1227-1298)
+template <int NV>
+__global__ void __launch_bounds__(128) block_residual_kernel(const double *__restrict__ A, const double *__restrict__ B,
+                                                             const double *__restrict__ X, const double *__restrict__ rhs,
+                                                             double *__restrict__ out, int64_t n) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * NV) return;
+    const int64_t j = idx / NV;
+    const int i = (int)(idx - j * NV);
+    const double *a = A + (j * NV + i) * NV;
+    double s = rhs[idx];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) s = fma(-a[c], X[j * NV + c], s);
+    if (B) {
+        const double *b = B + (j * NV + i) * NV;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) s = fma(-b[c], X[(j + 1) * NV + c], s);
+    } else {
+        s -= X[(j + 1) * NV + i];
+    }
+    out[idx] = s;
+}
+
+__global__ void __launch_bounds__(256) axpy_kernel(double *__restrict__ x, const double *__restrict__ d, double alpha,
+                                                   int64_t total) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x)
+        x[idx] = fma(alpha, d[idx], x[idx]);
+}
+
+}  // namespace rst

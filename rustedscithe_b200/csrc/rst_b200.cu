@@ -1,0 +1,998 @@
+// rst_b200.cu -- C ABI (include/rst_b200.h) over the sm_100a kernels: problem registry, device-resident
+// solver handle, recursive condensation orchestration, damped Newton host loop.
+//
+// Host-side restatement of (paths relative to the reference root):
+//   NRBVP::step / damped_step / try_main_loop_damped   src/numerical/BVP_Damp/NR_Damp_solver_damped.rs:1782-2156
+//   jac_recalc                                          src/numerical/BVP_Damp/BVP_utils_damped.rs:185-207
+//   unknown layout / BC elimination                     src/numerical/BVP_Damp/numeric_discretization.rs:27-136
+// There is deliberately no CPU fallback anywhere in this file.
+#include "../../include/rst_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "abd.cuh"
+#include "assemble.cuh"
+#include "newton.cuh"
+#include "generated/generated_problems.cuh"
+
+using namespace rst;
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(RST_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// problem registry: one entry per struct the CUDA-C emitter generated
+// ------------------------------------------------------------------------------------------------
+struct ProblemVT {
+    const char *key;
+    int nv, np;
+    const char *hash;
+    const unsigned char *pattern;
+    void (*assemble)(const AsmArgs &, bool with_j, bool trapezoid, cudaStream_t);
+};
+
+template <class P>
+static void launch_assemble(const AsmArgs &a, bool with_j, bool trap, cudaStream_t st) {
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((a.n + threads - 1) / threads);
+    if (blocks == 0) return;
+    if (!trap) {
+        if (with_j) assemble_kernel<P, true, false><<<blocks, threads, 0, st>>>(a);
+        else assemble_kernel<P, false, false><<<blocks, threads, 0, st>>>(a);
+    } else {
+        if (with_j) assemble_kernel<P, true, true><<<blocks, threads, 0, st>>>(a);
+        else assemble_kernel<P, false, true><<<blocks, threads, 0, st>>>(a);
+    }
+}
+
+static const ProblemVT g_problems[] = {
+#define RST_PROBLEM(P, H) {P::key(), P::NV, P::NP, H, P::pattern(), &launch_assemble<P>},
+#include "generated/generated_registry.inc"
+#undef RST_PROBLEM
+};
+static const int g_nproblems = (int)(sizeof(g_problems) / sizeof(g_problems[0]));
+
+static const ProblemVT *find_problem(const char *key) {
+    if (!key) return nullptr;
+    for (int i = 0; i < g_nproblems; ++i)
+        if (std::strcmp(g_problems[i].key, key) == 0) return &g_problems[i];
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-size dispatch of the solver kernels
+// ------------------------------------------------------------------------------------------------
+struct SolverVT {
+    int nv;
+    void (*factor)(const AbdLevel &, bool ident_b, unsigned *flags, cudaStream_t);
+    void (*forward)(const AbdLevel &, cudaStream_t);
+    void (*backward)(const AbdLevel &, cudaStream_t);
+    void (*top)(const double *C, const double *D, const double *g, double *Z, unsigned long long lm,
+                unsigned long long rm, unsigned *flags, cudaStream_t);
+    void (*residual)(const double *A, const double *B, const double *X, const double *rhs, double *out, int64_t n,
+                     cudaStream_t);
+};
+
+template <int NV>
+struct SolverImpl {
+    static unsigned grid_for(int64_t nslabs, int lanes) {
+        const int gpw = 32 / next_pow2(lanes);
+        const int64_t per_block = 4 * gpw;
+        return (unsigned)((nslabs + per_block - 1) / per_block);
+    }
+    static void factor(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
+        const unsigned blocks = grid_for(L.nslabs, 2 * NV);
+        if (ident_b) abd_factor_kernel<NV, true><<<blocks, 128, 0, st>>>(L, flags);
+        else abd_factor_kernel<NV, false><<<blocks, 128, 0, st>>>(L, flags);
+    }
+    static void forward(const AbdLevel &L, cudaStream_t st) {
+        abd_forward_kernel<NV><<<grid_for(L.nslabs, 2 * NV), 128, 0, st>>>(L);
+    }
+    static void backward(const AbdLevel &L, cudaStream_t st) {
+        abd_backward_kernel<NV><<<grid_for(L.nslabs, NV), 128, 0, st>>>(L);
+    }
+    static void top(const double *C, const double *D, const double *g, double *Z, unsigned long long lm,
+                    unsigned long long rm, unsigned *flags, cudaStream_t st) {
+        abd_top_solve_kernel<NV><<<1, 32, 0, st>>>(C, D, g, Z, lm, rm, flags);
+    }
+    static void residual(const double *A, const double *B, const double *X, const double *rhs, double *out, int64_t n,
+                         cudaStream_t st) {
+        const int64_t total = n * NV;
+        block_residual_kernel<NV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(A, B, X, rhs, out, n);
+    }
+    static SolverVT vt() { return SolverVT{NV, &factor, &forward, &backward, &top, &residual}; }
+};
+
+static bool solver_vt_for(int nv, SolverVT *out) {
+    switch (nv) {
+        case 2: *out = SolverImpl<2>::vt(); return true;
+        case 6: *out = SolverImpl<6>::vt(); return true;
+        case 8: *out = SolverImpl<8>::vt(); return true;
+        case 12: *out = SolverImpl<12>::vt(); return true;
+        default: return false;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// solver handle
+// ------------------------------------------------------------------------------------------------
+struct LevelBuf {
+    AbdLevel k;
+    bool ident_b;
+};
+
+struct rst_b200_solver {
+    const ProblemVT *pb = nullptr;
+    SolverVT sv{};
+    int nv = 0, np = 0, scheme = 0, trap_time = 0, device = 0;
+    int rank = 0, world = 1;
+    int64_t N = 0;         // global intervals
+    int64_t n = 0;         // local intervals
+    int64_t j_begin = 0;
+    double t0 = 0, t_end = 1, h = 0;
+    bool uniform = true;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // BC layout (global)
+    unsigned long long left_mask = 0, right_mask = 0;
+    std::vector<double> left_val, right_val;  // per component (valid where masked)
+    LayoutArgs layout{};
+    // device buffers
+    double *Y = nullptr, *Yt = nullptr, *F = nullptr, *A = nullptr, *B = nullptr, *dY = nullptr;
+    double *d_mesh = nullptr, *d_params = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_rtol = nullptr;
+    double *d_tmp = nullptr;  // [n*nv + nv] staging for reduced-order host drop-ins
+    std::vector<void *> owned;
+    std::vector<LevelBuf> levels;      // local condensation levels
+    bool have_red = false;
+    LevelBuf red{};                    // interface (reduced) level when world > 1
+    double *iface_rows = nullptr;      // [2 nv^2]  (A | B) of the local condensed row
+    double *iface_rhs = nullptr;       // [nv]
+    double *gath_rows = nullptr;       // [world][2 nv^2]
+    double *gath_rhs = nullptr;        // [world][nv]
+    double *redA = nullptr, *redB = nullptr, *red_r = nullptr, *Zred = nullptr;
+    double *topA = nullptr, *topB = nullptr, *top_r = nullptr, *Ztop = nullptr;
+    // reductions
+    int red_blocks = 0;
+    double *d_partials = nullptr, *d_scal = nullptr, *d_gscal = nullptr;
+    double *h_scal = nullptr;  // pinned
+    unsigned *d_flags = nullptr;
+    // value-stream map for the legacy AOT ABI
+    std::vector<int64_t> st_rows, st_cols;
+    int st_kl = 0, st_ku = 0;
+    int64_t *d_stream_src = nullptr;
+    double *d_stream_out = nullptr;
+    bool have_jac = false, factored = false;
+    rst_b200_allgather_fn allgather = nullptr;
+    void *allgather_ctx = nullptr;
+    int64_t launches = 0;
+    cudaEvent_t ev[2]{};
+};
+
+static rst_b200_solver *g_bound = nullptr;  // handle behind the reference's handle-less AOT symbols
+
+template <class T>
+static int dev_alloc(rst_b200_solver *s, T **p, size_t count) {
+    void *q = nullptr;
+    if (count == 0) count = 1;
+    CUDA_TRY(cudaMalloc(&q, count * sizeof(T)));
+    s->owned.push_back(q);
+    *p = (T *)q;
+    return RST_B200_OK;
+}
+#define TRY(expr)                     \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != RST_B200_OK) return _rc; \
+    } while (0)
+
+static int default_slab(int64_t n, int requested) {
+    if (requested >= 2) return requested;
+    if (n >= (1 << 17)) return 32;
+    if (n >= (1 << 12)) return 16;
+    return 8;
+}
+
+static int build_level(rst_b200_solver *s, LevelBuf *lv, int64_t n, int S, const double *A, const double *B,
+                       const double *r, double *Z) {
+    const int nv = s->nv;
+    AbdLevel &k = lv->k;
+    k.n = n;
+    k.S = S;
+    k.nslabs = (n + S - 1) / S;
+    k.A = A;
+    k.B = B;
+    k.r = r;
+    k.Z = Z;
+    lv->ident_b = (B == nullptr);
+    TRY(dev_alloc(s, &k.Lm, (size_t)n * nv * 2 * nv));
+    TRY(dev_alloc(s, &k.UEF, (size_t)n * 3 * nv * nv));
+    TRY(dev_alloc(s, &k.piv, (size_t)n * 2 * nv));
+    TRY(dev_alloc(s, &k.e, (size_t)n * nv));
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_version(void) { return 1; }
+extern "C" int rst_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+extern "C" int rst_b200_problem_count(void) { return g_nproblems; }
+extern "C" const char *rst_b200_problem_key(int i) { return (i >= 0 && i < g_nproblems) ? g_problems[i].key : nullptr; }
+extern "C" int rst_b200_problem_info(const char *key, int *nv, int *np, const char **hash) {
+    const ProblemVT *p = find_problem(key);
+    if (!p) return fail(RST_B200_ERR_UNSUPPORTED, "unknown problem key");
+    if (nv) *nv = p->nv;
+    if (np) *np = p->np;
+    if (hash) *hash = p->hash;
+    return RST_B200_OK;
+}
+extern "C" const char *rst_b200_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
+    if (!d || !out) return fail(RST_B200_ERR_INVALID, "null descriptor");
+    *out = nullptr;
+    const ProblemVT *pb = find_problem(d->problem_key);
+    if (!pb) return fail(RST_B200_ERR_UNSUPPORTED, std::string("problem key not compiled in: ") + (d->problem_key ? d->problem_key : "(null)"));
+    const int nv = pb->nv;
+    if (d->n_steps < 2) return fail(RST_B200_ERR_INVALID, "n_steps must be >= 2");  // numeric_discretization.rs:156
+    if (d->n_bc != nv) return fail(RST_B200_ERR_INVALID, "expects exactly nv total boundary conditions");  // :60-67
+    if (d->n_params != pb->np) return fail(RST_B200_ERR_INVALID, "parameter count mismatch");
+    if (!d->lo || !d->hi || !d->rtol || !d->bc_var || !d->bc_side || !d->bc_val)
+        return fail(RST_B200_ERR_INVALID, "missing bounds / tolerances / boundary conditions");
+    const int world = d->world > 0 ? d->world : 1;
+    if (d->rank < 0 || d->rank >= world) return fail(RST_B200_ERR_INVALID, "rank out of range");
+    if (d->n_steps < 2 * (int64_t)world) return fail(RST_B200_ERR_INVALID, "fewer than 2 intervals per rank");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(RST_B200_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(d->device));
+
+    rst_b200_solver *s = new rst_b200_solver();
+    s->pb = pb;
+    s->nv = nv;
+    s->np = pb->np;
+    if (!solver_vt_for(nv, &s->sv)) {
+        delete s;
+        return fail(RST_B200_ERR_UNSUPPORTED, "block size not compiled in");
+    }
+    s->scheme = d->scheme;
+    s->trap_time = d->trap_time;
+    s->device = d->device;
+    s->rank = d->rank;
+    s->world = world;
+    s->N = d->n_steps;
+    s->j_begin = (d->n_steps * (int64_t)d->rank) / world;
+    const int64_t j_end = (d->n_steps * (int64_t)(d->rank + 1)) / world;
+    s->n = j_end - s->j_begin;
+    s->t0 = d->t0;
+    s->t_end = d->t_end;
+    s->h = (d->t_end - d->t0) / (double)d->n_steps;
+    s->uniform = (d->mesh == nullptr);
+    s->left_val.assign(nv, 0.0);
+    s->right_val.assign(nv, 0.0);
+    for (int k = 0; k < d->n_bc; ++k) {
+        const int v = d->bc_var[k];
+        if (v < 0 || v >= nv) { delete s; return fail(RST_B200_ERR_INVALID, "boundary variable index out of range"); }
+        if (d->bc_side[k] == 0) {
+            if ((s->left_mask >> v) & 1ull) { delete s; return fail(RST_B200_ERR_INVALID, "duplicate boundary condition"); }
+            s->left_mask |= 1ull << v;
+            s->left_val[v] = d->bc_val[k];
+        } else if (d->bc_side[k] == 1) {
+            if ((s->right_mask >> v) & 1ull) { delete s; return fail(RST_B200_ERR_INVALID, "duplicate boundary condition"); }
+            s->right_mask |= 1ull << v;
+            s->right_val[v] = d->bc_val[k];
+        } else {
+            delete s;
+            return fail(RST_B200_ERR_INVALID, "boundary side flag must be 0 or 1");
+        }
+    }
+    LayoutArgs &la = s->layout;
+    la.n_steps = s->N;
+    la.nv = nv;
+    la.nl = la.nr = 0;
+    {
+        int a = 0, b = 0;
+        for (int v = 0; v < nv; ++v) {
+            if ((s->left_mask >> v) & 1ull) la.nl++; else la.left_free[a++] = v;
+            if ((s->right_mask >> v) & 1ull) la.nr++; else la.right_free[b++] = v;
+        }
+    }
+    if (d->stream) s->stream = (cudaStream_t)d->stream;
+    else {
+        if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail(RST_B200_ERR_CUDA, "stream"); }
+        s->own_stream = true;
+    }
+    cudaEventCreate(&s->ev[0]);
+    cudaEventCreate(&s->ev[1]);
+
+    int rc = RST_B200_OK;
+    auto build = [&]() -> int {
+        const int64_t n = s->n;
+        const size_t nodes = (size_t)(n + 1) * nv;
+        TRY(dev_alloc(s, &s->Y, nodes));
+        TRY(dev_alloc(s, &s->Yt, nodes));
+        TRY(dev_alloc(s, &s->dY, nodes));
+        TRY(dev_alloc(s, &s->F, (size_t)n * nv));
+        TRY(dev_alloc(s, &s->A, (size_t)n * nv * nv));
+        if (s->scheme == RST_B200_SCHEME_TRAPEZOID) TRY(dev_alloc(s, &s->B, (size_t)n * nv * nv));
+        TRY(dev_alloc(s, &s->d_tmp, nodes + nv));
+        TRY(dev_alloc(s, &s->d_params, (size_t)(s->np > 0 ? s->np : 1)));
+        TRY(dev_alloc(s, &s->d_lo, (size_t)nv));
+        TRY(dev_alloc(s, &s->d_hi, (size_t)nv));
+        TRY(dev_alloc(s, &s->d_rtol, (size_t)nv));
+        TRY(dev_alloc(s, &s->d_flags, (size_t)4));
+        CUDA_TRY(cudaMemsetAsync(s->d_flags, 0, 4 * sizeof(unsigned), s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->Y, 0, nodes * sizeof(double), s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->Yt, 0, nodes * sizeof(double), s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->dY, 0, nodes * sizeof(double), s->stream));
+        if (s->np > 0) CUDA_TRY(cudaMemcpyAsync(s->d_params, d->params, s->np * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->d_lo, d->lo, nv * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->d_hi, d->hi, nv * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->d_rtol, d->rtol, nv * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        if (!s->uniform) {
+            TRY(dev_alloc(s, &s->d_mesh, (size_t)(n + 1)));
+            CUDA_TRY(cudaMemcpyAsync(s->d_mesh, d->mesh + s->j_begin, (n + 1) * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        }
+        // interface + top buffers
+        TRY(dev_alloc(s, &s->iface_rows, (size_t)2 * nv * nv));
+        TRY(dev_alloc(s, &s->iface_rhs, (size_t)nv));
+        TRY(dev_alloc(s, &s->Ztop, (size_t)2 * nv));
+        if (world > 1) {
+            TRY(dev_alloc(s, &s->gath_rows, (size_t)world * 2 * nv * nv));
+            TRY(dev_alloc(s, &s->gath_rhs, (size_t)world * nv));
+            TRY(dev_alloc(s, &s->redA, (size_t)world * nv * nv));
+            TRY(dev_alloc(s, &s->redB, (size_t)world * nv * nv));
+            TRY(dev_alloc(s, &s->red_r, (size_t)world * nv));
+            TRY(dev_alloc(s, &s->Zred, (size_t)(world + 1) * nv));
+            TRY(dev_alloc(s, &s->topA, (size_t)nv * nv));
+            TRY(dev_alloc(s, &s->topB, (size_t)nv * nv));
+            TRY(dev_alloc(s, &s->top_r, (size_t)nv));
+        }
+        // local condensation levels: n -> ceil(n/S) -> ... -> 1
+        {
+            int64_t ln = n;
+            const double *lA = s->A, *lB = s->B, *lr = s->F;
+            double *lZ = s->dY;
+            int depth = 0;
+            while (ln > 1) {
+                LevelBuf lv{};
+                const int S = default_slab(ln, depth == 0 ? d->slab : 0);
+                TRY(build_level(s, &lv, ln, S, lA, lB, lr, lZ));
+                const int64_t nn = lv.k.nslabs;
+                if (nn > 1) {
+                    TRY(dev_alloc(s, &lv.k.A_next, (size_t)nn * nv * nv));
+                    TRY(dev_alloc(s, &lv.k.B_next, (size_t)nn * nv * nv));
+                    TRY(dev_alloc(s, &lv.k.r_next, (size_t)nn * nv));
+                    double *zn = nullptr;
+                    TRY(dev_alloc(s, &zn, (size_t)(nn + 1) * nv));
+                    lv.k.Z_next = zn;
+                } else {  // last local level feeds the interface row
+                    lv.k.A_next = s->iface_rows;
+                    lv.k.B_next = s->iface_rows + nv * nv;
+                    lv.k.r_next = s->iface_rhs;
+                    lv.k.Z_next = (world > 1) ? (s->Zred + (size_t)s->rank * nv) : s->Ztop;
+                }
+                s->levels.push_back(lv);
+                lA = lv.k.A_next;
+                lB = lv.k.B_next;
+                lr = lv.k.r_next;
+                lZ = const_cast<double *>(lv.k.Z_next);
+                ln = nn;
+                ++depth;
+            }
+        }
+        if (world > 1) {
+            LevelBuf lv{};
+            TRY(build_level(s, &lv, world, world, s->redA, s->redB, s->red_r, s->Zred));
+            lv.k.A_next = s->topA;
+            lv.k.B_next = s->topB;
+            lv.k.r_next = s->top_r;
+            lv.k.Z_next = s->Ztop;
+            s->red = lv;
+            s->have_red = true;
+        }
+        // reductions
+        s->red_blocks = 148 * 4;
+        TRY(dev_alloc(s, &s->d_partials, (size_t)s->red_blocks * 4));
+        TRY(dev_alloc(s, &s->d_scal, (size_t)8));
+        TRY(dev_alloc(s, &s->d_gscal, (size_t)8 * world));
+        CUDA_TRY(cudaMallocHost((void **)&s->h_scal, 8 * sizeof(double)));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        return RST_B200_OK;
+    };
+    rc = build();
+    if (rc != RST_B200_OK) {
+        rst_b200_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return RST_B200_OK;
+}
+
+extern "C" void rst_b200_destroy(rst_b200_solver *s) {
+    if (!s) return;
+    if (g_bound == s) g_bound = nullptr;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (void *p : s->owned) cudaFree(p);
+    if (s->h_scal) cudaFreeHost(s->h_scal);
+    if (s->ev[0]) cudaEventDestroy(s->ev[0]);
+    if (s->ev[1]) cudaEventDestroy(s->ev[1]);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" int64_t rst_b200_n_unknowns(const rst_b200_solver *s) { return s ? s->n * s->nv : 0; }
+extern "C" int rst_b200_memcpy(void *dst, const void *src, size_t bytes, int kind) {
+    if (!dst || !src || kind < 1 || kind > 3) return fail(RST_B200_ERR_INVALID, "bad memcpy arguments");
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(dst, src, bytes, (cudaMemcpyKind)kind));
+    return RST_B200_OK;
+}
+extern "C" int64_t rst_b200_launch_count(const rst_b200_solver *s) { return s ? s->launches : 0; }
+extern "C" int rst_b200_sync(rst_b200_solver *s) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return RST_B200_OK;
+}
+extern "C" int rst_b200_set_params(rst_b200_solver *s, const double *params, int n_params) {
+    if (!s || n_params != s->np || (n_params > 0 && !params)) return fail(RST_B200_ERR_INVALID, "parameter count mismatch");
+    if (s->np > 0) {
+        CUDA_TRY(cudaMemcpyAsync(s->d_params, params, s->np * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    s->have_jac = s->factored = false;
+    return RST_B200_OK;
+}
+extern "C" int rst_b200_set_allgather(rst_b200_solver *s, rst_b200_allgather_fn fn, void *ctx) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    s->allgather = fn;
+    s->allgather_ctx = ctx;
+    return RST_B200_OK;
+}
+extern "C" int rst_b200_dist_range(const rst_b200_solver *s, int64_t *b, int64_t *e) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    if (b) *b = s->j_begin;
+    if (e) *e = s->j_begin + s->n;
+    return RST_B200_OK;
+}
+
+extern "C" void *rst_b200_device_ptr(rst_b200_solver *s, int which) {
+    if (!s) return nullptr;
+    switch (which) {
+        case 0: return s->Y;
+        case 1: return s->F;
+        case 2: return s->A;
+        case 3: return s->B;
+        case 4: return s->dY;
+        case 5: return s->Yt;
+        case 6: return s->iface_rows;
+        case 7: return s->iface_rhs;
+        case 8: return s->gath_rows;
+        case 9: return s->gath_rhs;
+        case 10: return s->d_scal;
+        case 11: return s->d_gscal;
+        default: return nullptr;
+    }
+}
+
+// ---- state movement ---------------------------------------------------------------------------
+// global reduced index of (global node g, component v), or -1 for a pinned slot (numeric_discretization.rs:80-106)
+static inline int64_t reduced_index(const rst_b200_solver *s, int64_t g, int v) {
+    const int nv = s->nv;
+    if (g == 0) {
+        if ((s->left_mask >> v) & 1ull) return -1;
+        int k = 0;
+        for (int c = 0; c < v; ++c) k += !((s->left_mask >> c) & 1ull);
+        return k;
+    }
+    if (g == s->N) {
+        if ((s->right_mask >> v) & 1ull) return -1;
+        int k = 0;
+        for (int c = 0; c < v; ++c) k += !((s->right_mask >> c) & 1ull);
+        return s->N * (int64_t)nv - s->layout.nl + k;
+    }
+    return g * (int64_t)nv + v - s->layout.nl;
+}
+
+extern "C" int rst_b200_set_state(rst_b200_solver *s, const double *y, size_t len) {
+    if (!s || !y) return fail(RST_B200_ERR_INVALID, "null argument");
+    if ((int64_t)len != s->N * (int64_t)s->nv) return fail(RST_B200_ERR_INVALID, "reduced state length mismatch");
+    const int nv = s->nv;
+    if (s->world == 1) {
+        // one H2D copy of the reduced vector, expansion on the device
+        CUDA_TRY(cudaMemcpyAsync(s->d_tmp, y, len * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        scatter_reduced_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->layout, s->d_tmp, s->Y);
+        s->launches++;
+        double pins[128];
+        for (int v = 0; v < nv; ++v) { pins[v] = s->left_val[v]; pins[nv + v] = s->right_val[v]; }
+        for (int v = 0; v < nv; ++v) {
+            if ((s->left_mask >> v) & 1ull)
+                CUDA_TRY(cudaMemcpyAsync(s->Y + v, &pins[v], sizeof(double), cudaMemcpyHostToDevice, s->stream));
+            if ((s->right_mask >> v) & 1ull)
+                CUDA_TRY(cudaMemcpyAsync(s->Y + s->N * nv + v, &pins[nv + v], sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    } else {
+        std::vector<double> full((size_t)(s->n + 1) * nv);
+        for (int64_t i = 0; i <= s->n; ++i) {
+            const int64_t g = s->j_begin + i;
+            for (int v = 0; v < nv; ++v) {
+                const int64_t k = reduced_index(s, g, v);
+                full[i * nv + v] = k >= 0 ? y[k] : (g == 0 ? s->left_val[v] : s->right_val[v]);
+            }
+        }
+        CUDA_TRY(cudaMemcpyAsync(s->Y, full.data(), full.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    s->have_jac = s->factored = false;
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_get_state(rst_b200_solver *s, double *y, size_t len) {
+    if (!s || !y) return fail(RST_B200_ERR_INVALID, "null argument");
+    if ((int64_t)len != s->N * (int64_t)s->nv) return fail(RST_B200_ERR_INVALID, "reduced state length mismatch");
+    const int nv = s->nv;
+    if (s->world == 1) {
+        gather_reduced_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->layout, s->Y, s->d_tmp);
+        s->launches++;
+        CUDA_TRY(cudaMemcpyAsync(y, s->d_tmp, len * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    } else {
+        std::vector<double> full((size_t)(s->n + 1) * nv);
+        CUDA_TRY(cudaMemcpyAsync(full.data(), s->Y, full.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        const int64_t last = (s->rank == s->world - 1) ? s->n : s->n - 1;  // owned nodes
+        for (int64_t i = 0; i <= last; ++i) {
+            const int64_t g = s->j_begin + i;
+            for (int v = 0; v < nv; ++v) {
+                const int64_t k = reduced_index(s, g, v);
+                if (k >= 0) y[k] = full[i * nv + v];
+            }
+        }
+    }
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_get_full_solution(rst_b200_solver *s, double *full, size_t len) {
+    if (!s || !full) return fail(RST_B200_ERR_INVALID, "null argument");
+    if ((int64_t)len != (s->N + 1) * (int64_t)s->nv) return fail(RST_B200_ERR_INVALID, "full solution length mismatch");
+    const int64_t owned = (s->rank == s->world - 1) ? s->n + 1 : s->n;
+    CUDA_TRY(cudaMemcpyAsync(full + s->j_begin * s->nv, s->Y, (size_t)owned * s->nv * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return RST_B200_OK;
+}
+
+// ---- hot path ------------------------------------------------------------------------------------
+static int assemble(rst_b200_solver *s, int which_state, bool with_j) {
+    AsmArgs a{};
+    a.Y = which_state ? s->Yt : s->Y;
+    a.F = s->F;
+    a.A = s->A;
+    a.B = s->B;
+    a.mesh = s->uniform ? nullptr : s->d_mesh;
+    a.params = s->d_params;
+    a.t0 = s->t0;
+    a.h = s->h;
+    a.n = s->n;
+    a.j_offset = s->j_begin;
+    a.trap_time = s->trap_time;
+    s->pb->assemble(a, with_j, s->scheme == RST_B200_SCHEME_TRAPEZOID, s->stream);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_eval_residual(rst_b200_solver *s, int which_state) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    return assemble(s, which_state, false);
+}
+extern "C" int rst_b200_eval_jacobian(rst_b200_solver *s, int which_state) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    TRY(assemble(s, which_state, true));
+    s->have_jac = true;
+    s->factored = false;
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_factor_local(rst_b200_solver *s) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    if (!s->have_jac) return fail(RST_B200_ERR_NOT_FACTORIZED, "no Jacobian has been evaluated");
+    CUDA_TRY(cudaMemsetAsync(s->d_flags, 0, sizeof(unsigned), s->stream));
+    for (auto &lv : s->levels) {
+        s->sv.factor(lv.k, lv.ident_b, s->d_flags, s->stream);
+        s->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return RST_B200_OK;
+}
+
+__global__ void split_rows_kernel(const double *gath, double *A, double *B, int world, int nvnv) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= world * nvnv) return;
+    const int p = idx / nvnv, e = idx % nvnv;
+    A[idx] = gath[(size_t)p * 2 * nvnv + e];
+    B[idx] = gath[(size_t)p * 2 * nvnv + nvnv + e];
+}
+
+extern "C" int rst_b200_factor_reduced(rst_b200_solver *s) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    if (s->have_red) {
+        const int nvnv = s->nv * s->nv;
+        split_rows_kernel<<<(s->world * nvnv + 127) / 128, 128, 0, s->stream>>>(s->gath_rows, s->redA, s->redB, s->world, nvnv);
+        s->sv.factor(s->red.k, false, s->d_flags, s->stream);
+        s->launches += 2;
+    }
+    CUDA_TRY(cudaGetLastError());
+    s->factored = true;
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_factor(rst_b200_solver *s) {
+    TRY(rst_b200_factor_local(s));
+    if (s->world > 1) {
+        if (!s->allgather) return fail(RST_B200_ERR_INVALID, "world > 1 needs rst_b200_set_allgather");
+        if (s->allgather(s->allgather_ctx, s->iface_rows, s->gath_rows, 2 * (int64_t)s->nv * s->nv, s->stream) != 0)
+            return fail(RST_B200_ERR_CUDA, "all-gather callback failed");
+    }
+    return rst_b200_factor_reduced(s);
+}
+
+extern "C" int rst_b200_solve_local_forward(rst_b200_solver *s) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    if (!s->factored) return fail(RST_B200_ERR_NOT_FACTORIZED, "solve before factor");
+    for (auto &lv : s->levels) {
+        s->sv.forward(lv.k, s->stream);
+        s->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    const double *C, *D, *g;
+    if (s->have_red) {
+        CUDA_TRY(cudaMemcpyAsync(s->red_r, s->gath_rhs, (size_t)s->world * s->nv * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        s->sv.forward(s->red.k, s->stream);
+        s->launches++;
+        C = s->topA; D = s->topB; g = s->top_r;
+    } else {
+        C = s->iface_rows; D = s->iface_rows + s->nv * s->nv; g = s->iface_rhs;
+    }
+    s->sv.top(C, D, g, s->Ztop, s->left_mask, s->right_mask, s->d_flags, s->stream);
+    s->launches++;
+    if (s->have_red) {
+        s->sv.backward(s->red.k, s->stream);
+        s->launches++;
+    }
+    for (int i = (int)s->levels.size() - 1; i >= 0; --i) {
+        s->sv.backward(s->levels[i].k, s->stream);
+        s->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_solve(rst_b200_solver *s) {
+    TRY(rst_b200_solve_local_forward(s));
+    if (s->world > 1) {
+        if (!s->allgather) return fail(RST_B200_ERR_INVALID, "world > 1 needs rst_b200_set_allgather");
+        if (s->allgather(s->allgather_ctx, s->iface_rhs, s->gath_rhs, (int64_t)s->nv, s->stream) != 0)
+            return fail(RST_B200_ERR_CUDA, "all-gather callback failed");
+    }
+    return rst_b200_solve_reduced_backward(s);
+}
+
+__global__ void combine_scalars_kernel(const double *g, int world, double *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double a0 = 0.0, a1 = 0.0, a2 = 1.0, a3 = 0.0, a4 = 0.0;
+    for (int p = 0; p < world; ++p) {
+        a0 += g[8 * p]; a1 += g[8 * p + 1]; a2 = fmin(a2, g[8 * p + 2]); a3 = fmax(a3, g[8 * p + 3]); a4 = fmax(a4, g[8 * p + 4]);
+    }
+    out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3; out[4] = a4;
+}
+
+extern "C" int rst_b200_reduce_local(rst_b200_solver *s, int which_state) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    ReduceArgs a{};
+    a.Y = which_state ? s->Yt : s->Y;
+    a.dY = s->dY;
+    a.F = s->F;
+    a.lo = s->d_lo; a.hi = s->d_hi; a.rtol = s->d_rtol;
+    // ranks own nodes [0, n) of their slab; the last rank also owns global node N
+    a.n_nodes = (s->rank == s->world - 1) ? s->n + 1 : s->n;
+    a.nv = s->nv;
+    a.left_mask = s->left_mask; a.right_mask = s->right_mask;
+    a.has_left = (s->rank == 0); a.has_right = (s->rank == s->world - 1);
+    a.partials = s->d_partials;
+    a.n_rows = s->n;
+    newton_reduce_kernel<<<s->red_blocks, 256, 0, s->stream>>>(a);
+    newton_reduce_final_kernel<<<1, 256, 0, s->stream>>>(s->d_partials, s->red_blocks, s->d_scal, s->d_flags);
+    s->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_reduce_finish(rst_b200_solver *s, rst_b200_scalars *out) {
+    if (!s || !out) return fail(RST_B200_ERR_INVALID, "null argument");
+    const double *src = s->d_scal;
+    if (s->world > 1) {
+        combine_scalars_kernel<<<1, 32, 0, s->stream>>>(s->d_gscal, s->world, s->d_scal);
+        s->launches++;
+    }
+    CUDA_TRY(cudaMemcpyAsync(s->h_scal, src, 5 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    out->sumsq_step = s->h_scal[0];
+    out->tol_sum = s->h_scal[1];
+    out->fbound = s->h_scal[2];
+    out->nan_flag = s->h_scal[3];
+    out->device_flags = s->h_scal[4];
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_reduce(rst_b200_solver *s, int which_state, rst_b200_scalars *out) {
+    TRY(rst_b200_reduce_local(s, which_state));
+    if (s->world > 1) {
+        if (!s->allgather) return fail(RST_B200_ERR_INVALID, "world > 1 needs rst_b200_set_allgather");
+        if (s->allgather(s->allgather_ctx, s->d_scal, s->d_gscal, 8, s->stream) != 0)
+            return fail(RST_B200_ERR_CUDA, "all-gather callback failed");
+    }
+    return rst_b200_reduce_finish(s, out);
+}
+
+extern "C" int rst_b200_make_trial(rst_b200_solver *s, double lambda) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    const int64_t total = (s->n + 1) * (int64_t)s->nv;
+    newton_trial_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY, s->Yt, lambda, total);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_accept_trial(rst_b200_solver *s) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    std::swap(s->Y, s->Yt);
+    return RST_B200_OK;
+}
+
+// ---- damped Newton -------------------------------------------------------------------------------
+static int check_scalars(const rst_b200_scalars &sc) {
+    if (sc.nan_flag != 0.0) return fail(RST_B200_ERR_NAN, "NaN in residual or Newton step");
+    if (((unsigned)sc.device_flags) & RST_FLAG_ZERO_PIVOT) return fail(RST_B200_ERR_ZERO_PIVOT, "zero pivot in block elimination");
+    return RST_B200_OK;
+}
+
+// NRBVP::step (:1782-1847) for state `which`: dY = J^{-1} F(y)
+static int newton_step(rst_b200_solver *s, int which, rst_b200_newton_stats *st) {
+    TRY(rst_b200_eval_residual(s, which));
+    TRY(rst_b200_solve(s));
+    st->linear_solves++;
+    return RST_B200_OK;
+}
+
+static int recalc_jacobian(rst_b200_solver *s, rst_b200_newton_stats *st) {
+    TRY(rst_b200_eval_jacobian(s, 0));
+    TRY(rst_b200_factor(s));
+    st->jac_recalcs++;
+    st->factorizations++;
+    return RST_B200_OK;
+}
+
+// damped_step (:1862-2004).  Returns RST_B200_OK and the reference's status code in *status.
+static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b200_newton_stats *st, int *status) {
+    rst_b200_scalars sc{};
+    TRY(newton_step(s, 0, st));
+    TRY(rst_b200_reduce(s, 0, &sc));
+    TRY(check_scalars(sc));
+    const double fbound = sc.fbound;
+    st->last_fbound = fbound;
+    if (std::isnan(fbound) || std::isinf(fbound)) return fail(RST_B200_ERR_NAN, "boundary step factor is not finite");
+    double lambda = 1.0 * fbound;
+    if (fbound < 1e-10) { *status = -3; return RST_B200_OK; }
+    const double s0 = std::sqrt(sc.sumsq_step);
+    st->last_s0 = s0;
+    int k = 0;
+    bool accepted = false;
+    double s1 = 0.0, conv = 0.0;
+    while (k < o->max_damp_iter) {
+        TRY(rst_b200_make_trial(s, lambda));
+        TRY(newton_step(s, 1, st));
+        TRY(rst_b200_reduce(s, 1, &sc));
+        TRY(check_scalars(sc));
+        s1 = std::sqrt(sc.sumsq_step);
+        conv = sc.tol_sum > o->abs_tol ? sc.tol_sum : o->abs_tol;  // convergence_condition, BVP_utils_damped.rs:209-222
+        st->last_lambda = lambda;
+        if (s1 < 1.0 || s1 < s0) { accepted = true; break; }      // :1962
+        lambda = lambda / std::pow(2.0, (double)k + o->damp_factor); // :1971
+        k += 1;
+    }
+    st->last_s1 = s1;
+    st->last_conv = conv;
+    if (accepted) *status = (s1 > conv) ? 0 : 1;                   // :1983-1998
+    else *status = -2;
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_newton_iterate(rst_b200_solver *s, const rst_b200_newton_opts *o, int recalc,
+                                       rst_b200_newton_stats *st) {
+    if (!s || !o || !st) return fail(RST_B200_ERR_INVALID, "null argument");
+    if (recalc || !s->factored) TRY(recalc_jacobian(s, st));
+    st->iterations++;
+    int status = 0;
+    TRY(damped_step(s, o, st, &status));
+    if (status == 0 || status == 1) TRY(rst_b200_accept_trial(s));
+    st->status = status;
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_newton_solve(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b200_newton_stats *st) {
+    if (!s || !o || !st) return fail(RST_B200_ERR_INVALID, "null argument");
+    std::memset(st, 0, sizeof(*st));
+    cudaEventRecord(s->ev[0], s->stream);
+    bool have_jac = false, recalc = true;
+    int m = 0, n_jac_reeval = 0, it = 0, status = 0;
+    while (it < o->max_iterations) {
+        recalc = (!have_jac || m > o->max_jac) ? true : recalc;   // jac_recalc, BVP_utils_damped.rs:185-207
+        if (recalc) {                                              // recalc_jacobian :1746-1771
+            int rc = recalc_jacobian(s, st);
+            if (rc != RST_B200_OK) { st->status = rc; return rc; }
+            have_jac = true;
+            m = 0;
+        }
+        m += 1;
+        it += 1;
+        st->iterations++;
+        int rc = damped_step(s, o, st, &status);
+        if (rc != RST_B200_OK) { st->status = rc; return rc; }
+        if (status == 0) {
+            TRY(rst_b200_accept_trial(s));
+            recalc = false;
+        } else if (status == 1) {
+            TRY(rst_b200_accept_trial(s));
+            break;
+        } else {                                                   // :2119-2136
+            if (m > 1) {
+                recalc = true;
+                if (n_jac_reeval > 3) break;
+                n_jac_reeval += 1;
+            } else break;
+        }
+    }
+    cudaEventRecord(s->ev[1], s->stream);
+    cudaEventSynchronize(s->ev[1]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]);
+    st->ms_total = ms;
+    st->status = status;
+    return RST_B200_OK;
+}
+
+// ---- host-pointer drop-ins -----------------------------------------------------------------------
+extern "C" int rst_b200_solve_in_place(rst_b200_solver *s, double *rhs, size_t len) {
+    if (!s || !rhs) return fail(RST_B200_ERR_INVALID, "null argument");
+    if (s->world != 1) return fail(RST_B200_ERR_UNSUPPORTED, "host drop-in is single-GPU");
+    if (!s->factored) return fail(RST_B200_ERR_NOT_FACTORIZED, "solve before factor");
+    if ((int64_t)len != s->N * (int64_t)s->nv) return fail(RST_B200_ERR_INVALID, "rhs length mismatch");
+    // rows are interval-major already (row j*nv+i): rhs -> F, solve, gather dY in reduced column order
+    CUDA_TRY(cudaMemcpyAsync(s->F, rhs, len * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    TRY(rst_b200_solve(s));
+    gather_reduced_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->layout, s->dY, s->d_tmp);
+    s->launches++;
+    CUDA_TRY(cudaMemcpyAsync(rhs, s->d_tmp, len * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->h_scal, s->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    unsigned fl;
+    std::memcpy(&fl, s->h_scal, sizeof(unsigned));
+    if (fl & RST_FLAG_ZERO_PIVOT) return fail(RST_B200_ERR_ZERO_PIVOT, "zero pivot in block elimination");
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_solve_multiple_in_place(rst_b200_solver *s, double *rhs, size_t nrhs, size_t ldb) {
+    if (!s || !rhs) return fail(RST_B200_ERR_INVALID, "null argument");
+    const size_t n = (size_t)(s->N * (int64_t)s->nv);
+    if (ldb < n) return fail(RST_B200_ERR_INVALID, "ldb < n");  // BandedError::InvalidRhsLayout
+    for (size_t c = 0; c < nrhs; ++c) TRY(rst_b200_solve_in_place(s, rhs + c * ldb, n));
+    return RST_B200_OK;
+}
+
+// structure of the value stream, sorted by (row, col) (symbolic_functions_BVP.rs:1338-1359)
+static void build_structure(rst_b200_solver *s) {
+    if (!s->st_rows.empty()) return;
+    const int nv = s->nv;
+    const unsigned char *pat = s->pb->pattern;
+    const bool trap = s->scheme == RST_B200_SCHEME_TRAPEZOID;
+    int64_t kl = 0, ku = 0;
+    std::vector<int64_t> src;
+    for (int64_t j = 0; j < s->N; ++j)
+        for (int i = 0; i < nv; ++i) {
+            const int64_t row = j * nv + i;
+            for (int side = 0; side < 2; ++side)
+                for (int c = 0; c < nv; ++c) {
+                    const bool present = (side == 0 || trap) ? (c == i || pat[i * nv + c]) : (c == i);
+                    if (!present) continue;
+                    const int64_t col = reduced_index(s, j + side, c);
+                    if (col < 0) continue;
+                    s->st_rows.push_back(row);
+                    s->st_cols.push_back(col);
+                    const int64_t off = (j * nv + i) * (int64_t)nv + c;
+                    src.push_back(side == 0 ? off : (trap ? -(off + 2) : -1));
+                    if (col > row) ku = std::max(ku, col - row); else kl = std::max(kl, row - col);
+                }
+        }
+    s->st_kl = (int)kl;
+    s->st_ku = (int)ku;
+    if (cudaMalloc((void **)&s->d_stream_src, src.size() * sizeof(int64_t)) == cudaSuccess) {
+        s->owned.push_back(s->d_stream_src);
+        cudaMemcpy(s->d_stream_src, src.data(), src.size() * sizeof(int64_t), cudaMemcpyHostToDevice);
+    }
+    if (cudaMalloc((void **)&s->d_stream_out, src.size() * sizeof(double)) == cudaSuccess) s->owned.push_back(s->d_stream_out);
+}
+
+extern "C" int64_t rst_b200_jacobian_structure(rst_b200_solver *s, int64_t *rows, int64_t *cols, int64_t *doff,
+                                               int64_t *dpos, int *kl, int *ku) {
+    if (!s || s->world != 1) return -1;
+    build_structure(s);
+    const int64_t nnz = (int64_t)s->st_rows.size();
+    for (int64_t k = 0; k < nnz; ++k) {
+        if (rows) rows[k] = s->st_rows[k];
+        if (cols) cols[k] = s->st_cols[k];
+        const int64_t off = s->st_cols[k] - s->st_rows[k];
+        if (doff) doff[k] = off;
+        if (dpos) dpos[k] = off >= 0 ? s->st_rows[k] : s->st_cols[k];
+    }
+    if (kl) *kl = s->st_kl;
+    if (ku) *ku = s->st_ku;
+    return nnz;
+}
+
+extern "C" int rst_b200_aot_bind(rst_b200_solver *s) {
+    g_bound = s;
+    return RST_B200_OK;
+}
+
+// codegen_c_aot_library.rs:376-389: returns 1 ok / 0 on null pointers or out_len mismatch
+extern "C" int rustedscithe_aot_eval_residual(const double *args, size_t args_len, double *out, size_t out_len) {
+    rst_b200_solver *s = g_bound;
+    if (!s || !args || !out || s->world != 1) return 0;
+    const size_t n = (size_t)(s->N * (int64_t)s->nv);
+    if (out_len != n || args_len != n + (size_t)s->np) return 0;
+    if (s->np > 0 && cudaMemcpyAsync(s->d_params, args, s->np * sizeof(double), cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return 0;
+    if (rst_b200_set_state(s, args + s->np, n) != RST_B200_OK) return 0;
+    if (rst_b200_eval_residual(s, 0) != RST_B200_OK) return 0;
+    if (cudaMemcpyAsync(out, s->F, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) return 0;
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess) return 0;
+    return 1;
+}
+
+// codegen_c_aot_library.rs:391-409: nnz values in the manifest's entry order
+extern "C" int rustedscithe_aot_eval_jacobian_values(const double *args, size_t args_len, double *out, size_t out_len) {
+    rst_b200_solver *s = g_bound;
+    if (!s || !args || !out || s->world != 1) return 0;
+    const size_t n = (size_t)(s->N * (int64_t)s->nv);
+    build_structure(s);
+    const size_t nnz = s->st_rows.size();
+    if (out_len != nnz || args_len != n + (size_t)s->np || !s->d_stream_src || !s->d_stream_out) return 0;
+    if (s->np > 0 && cudaMemcpyAsync(s->d_params, args, s->np * sizeof(double), cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return 0;
+    if (rst_b200_set_state(s, args + s->np, n) != RST_B200_OK) return 0;
+    if (rst_b200_eval_jacobian(s, 0) != RST_B200_OK) return 0;
+    gather_values_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->d_stream_src, s->A, s->B, s->d_stream_out, (int64_t)nnz);
+    s->launches++;
+    if (cudaMemcpyAsync(out, s->d_stream_out, nnz * sizeof(double), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) return 0;
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess) return 0;
+    return 1;
+}

@@ -1,0 +1,262 @@
+"""Host-side mirror of the reference's solver interface for the damped BVP hot path, over the C ABI.
+
+Names and argument meaning follow the reference so parity tests read like its own tests:
+  NRBVP.new_with_options / try_solve / get_result / get_statistics
+      src/numerical/BVP_Damp/NR_Damp_solver_damped.rs:847, :2393, :2507, :1577-1689
+  Fun.call / Jac.call (residual / Jacobian callbacks)          BVP_traits.rs:459-461, :943-953
+  DirectLinearSolver.solve_in_place / solve_multiple_in_place  somelinalg/banded/solver_traits.rs:3-14
+Everything numerical happens in librst_b200.so on the GPU; this file only marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import lib as _lib
+from . import problems as _problems
+
+
+@dataclass
+class SolverParams:  # NR_Damp_solver_damped.rs:100-151
+    max_jac: int = 3
+    max_damp_iter: int = 5
+    damp_factor: float = 0.5
+
+
+@dataclass
+class DampedSolverOptions:  # NR_Damp_solver_damped.rs:155-178
+    strategy_params: SolverParams = field(default_factory=SolverParams)
+    abs_tolerance: float = 1e-6
+    rel_tolerance: dict | None = None
+    bounds: dict | None = None
+    max_iterations: int = 25
+    scheme: str = "forward"
+    trap_time: int = 0
+    slab: int = 0
+    device: int = 0
+    stream: int | None = None
+    rank: int = 0
+    world: int = 1
+
+    @classmethod
+    def from_spec(cls, spec, **kw):
+        return cls(strategy_params=SolverParams(spec.max_jac, spec.max_damp_iter, spec.damp_factor),
+                   abs_tolerance=spec.abs_tol, rel_tolerance=dict(spec.rtol), bounds=dict(spec.bounds),
+                   max_iterations=spec.max_iterations, **kw)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t=_lib.c_f64_p):
+    return a.ctypes.data_as(t)
+
+
+class NRBVP:
+    """Damped Newton BVP solver bound to one compiled-in AOT problem (device-resident state)."""
+
+    def __init__(self, problem, initial_guess, n_steps, options: DampedSolverOptions | None = None,
+                 t0=None, t_end=None, mesh=None, boundary_conditions=None, params=None):
+        self.spec = _problems.get(problem) if isinstance(problem, str) else problem
+        spec = self.spec
+        self.options = options or DampedSolverOptions.from_spec(spec)
+        o = self.options
+        self.L = _lib.load()
+        self.nv = spec.nv
+        self.n_steps = int(n_steps)
+        self.n = self.nv * self.n_steps
+        bcs = boundary_conditions if boundary_conditions is not None else spec.bcs
+        bc_list = []
+        for i, name in enumerate(spec.names):
+            for side, val in bcs.get(name, []):
+                bc_list.append((i, side, val))
+        bounds = o.bounds or spec.bounds
+        rtol = o.rel_tolerance or spec.rtol
+        self._keep = dict(
+            bc_var=np.array([b[0] for b in bc_list], dtype=np.int32),
+            bc_side=np.array([b[1] for b in bc_list], dtype=np.int32),
+            bc_val=_f64([b[2] for b in bc_list]),
+            lo=_f64([bounds[n][0] for n in spec.names]),
+            hi=_f64([bounds[n][1] for n in spec.names]),
+            rtol=_f64([rtol[n] for n in spec.names]),
+            params=_f64(params if params is not None else (spec.param_values or [0.0])),
+            mesh=_f64(mesh) if mesh is not None else None,
+            key=spec.key.encode(),
+        )
+        k = self._keep
+        if k["mesh"] is not None and k["mesh"].shape != (self.n_steps + 1,):
+            raise ValueError(f"mesh length mismatch: expected {self.n_steps + 1}, got {k['mesh'].shape[0]}")
+        d = _lib.Desc()
+        d.problem_key = k["key"]
+        d.n_steps = self.n_steps
+        d.scheme = 1 if o.scheme == "trapezoid" else 0
+        d.trap_time = o.trap_time
+        d.t0 = spec.t0 if t0 is None else t0
+        d.t_end = spec.t_end if t_end is None else t_end
+        d.mesh = _p(k["mesh"]) if k["mesh"] is not None else None
+        d.n_bc = len(bc_list)
+        d.bc_var = _p(k["bc_var"], _lib.c_int_p)
+        d.bc_side = _p(k["bc_side"], _lib.c_int_p)
+        d.bc_val = _p(k["bc_val"])
+        d.params = _p(k["params"])
+        d.n_params = len(spec.params)
+        d.lo, d.hi, d.rtol = _p(k["lo"]), _p(k["hi"]), _p(k["rtol"])
+        d.device = o.device
+        d.stream = o.stream
+        d.slab = o.slab
+        d.rank, d.world = o.rank, o.world
+        self.handle = C.c_void_p()
+        _lib.check(self.L.rst_b200_create(C.byref(d), C.byref(self.handle)))
+        self.stats = _lib.NewtonStats()
+        self.result = None
+        self._allgather_cb = None
+        if initial_guess is not None:
+            # column-major nv x n_steps guess flattened verbatim (NR_Damp_solver_damped.rs:2034-2040)
+            g = np.asarray(initial_guess, dtype=np.float64)
+            if g.ndim == 2:
+                g = g.reshape(-1, order="F")
+            self.set_state(g)
+
+    @classmethod
+    def new_with_options(cls, problem, initial_guess, n_steps, options=None, **kw):
+        return cls(problem, initial_guess, n_steps, options, **kw)
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.L.rst_b200_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- state ---------------------------------------------------------------------------------
+    def set_state(self, y_reduced):
+        y = _f64(y_reduced)
+        _lib.check(self.L.rst_b200_set_state(self.handle, _p(y), y.shape[0]))
+
+    def get_state(self):
+        y = np.zeros(self.n)
+        _lib.check(self.L.rst_b200_get_state(self.handle, _p(y), y.shape[0]))
+        return y
+
+    def set_params(self, params):
+        p = _f64(params)
+        _lib.check(self.L.rst_b200_set_params(self.handle, _p(p), p.shape[0]))
+
+    def device_ptr(self, which):
+        return self.L.rst_b200_device_ptr(self.handle, which)
+
+    def _opts(self):
+        o = self.options
+        return _lib.NewtonOpts(o.max_iterations, o.strategy_params.max_jac, o.strategy_params.max_damp_iter,
+                               o.strategy_params.damp_factor, o.abs_tolerance)
+
+    # -- reference solver surface -----------------------------------------------------------
+    def try_solve(self):
+        """try_solve -> try_main_loop_damped; returns the reduced solution or None (as the reference)."""
+        opts = self._opts()
+        rc = self.L.rst_b200_newton_solve(self.handle, C.byref(opts), C.byref(self.stats))
+        _lib.check(rc)
+        self.result = self.get_state() if self.stats.status == 1 else None
+        return self.result
+
+    def newton_iterate(self, recalc_jacobian=True):
+        opts = self._opts()
+        _lib.check(self.L.rst_b200_newton_iterate(self.handle, C.byref(opts), 1 if recalc_jacobian else 0,
+                                                  C.byref(self.stats)))
+        return self.stats.status
+
+    def get_result(self):
+        """(N+1) x nv matrix with boundary values re-inserted (NR_Damp_solver_damped.rs:2540-2558)."""
+        full = np.zeros((self.n_steps + 1) * self.nv)
+        _lib.check(self.L.rst_b200_get_full_solution(self.handle, _p(full), full.shape[0]))
+        return full.reshape(self.n_steps + 1, self.nv)
+
+    def get_statistics(self):
+        s = self.stats
+        return {"number of iterations": s.iterations, "number of solving linear systems": s.linear_solves,
+                "number of jacobians recalculations": s.jac_recalcs, "factorizations": s.factorizations,
+                "status": s.status, "ms_total": s.ms_total}
+
+    # -- Fun / Jac callbacks through the reference's AOT ABI (host pointers) -----------------
+    def fun_call(self, y_reduced, params=None):
+        p = _f64(params) if params is not None else (self._keep["params"] if self.spec.params else np.zeros(0))
+        args = np.concatenate([p, _f64(y_reduced)])
+        out = np.zeros(self.n)
+        self.L.rst_b200_aot_bind(self.handle)
+        ok = self.L.rustedscithe_aot_eval_residual(_p(args), args.shape[0], _p(out), out.shape[0])
+        if ok != 1:
+            raise _lib.RstB200Error(ok, "rustedscithe_aot_eval_residual returned 0")
+        return out
+
+    def jacobian_structure(self):
+        kl, ku = C.c_int(), C.c_int()
+        nnz = self.L.rst_b200_jacobian_structure(self.handle, None, None, None, None, C.byref(kl), C.byref(ku))
+        rows, cols, doff, dpos = (np.zeros(nnz, dtype=np.int64) for _ in range(4))
+        self.L.rst_b200_jacobian_structure(self.handle, _p(rows, _lib.c_i64_p), _p(cols, _lib.c_i64_p),
+                                           _p(doff, _lib.c_i64_p), _p(dpos, _lib.c_i64_p), C.byref(kl), C.byref(ku))
+        return rows, cols, doff, dpos, kl.value, ku.value
+
+    def jac_call(self, y_reduced, params=None):
+        p = _f64(params) if params is not None else (self._keep["params"] if self.spec.params else np.zeros(0))
+        args = np.concatenate([p, _f64(y_reduced)])
+        nnz = self.L.rst_b200_jacobian_structure(self.handle, None, None, None, None, None, None)
+        out = np.zeros(nnz)
+        self.L.rst_b200_aot_bind(self.handle)
+        ok = self.L.rustedscithe_aot_eval_jacobian_values(_p(args), args.shape[0], _p(out), out.shape[0])
+        if ok != 1:
+            raise _lib.RstB200Error(ok, "rustedscithe_aot_eval_jacobian_values returned 0")
+        return out
+
+    # -- DirectLinearSolver surface ---------------------------------------------------------
+    def factor(self):
+        _lib.check(self.L.rst_b200_factor(self.handle))
+
+    def solve_in_place(self, rhs):
+        x = _f64(rhs).copy()
+        _lib.check(self.L.rst_b200_solve_in_place(self.handle, _p(x), x.shape[0]))
+        return x
+
+    def solve_multiple_in_place(self, rhs, nrhs, ldb):
+        x = _f64(rhs).copy()
+        _lib.check(self.L.rst_b200_solve_multiple_in_place(self.handle, _p(x), nrhs, ldb))
+        return x
+
+    # -- device-resident primitives ------------------------------------------------------------
+    def eval_residual(self, which=0):
+        _lib.check(self.L.rst_b200_eval_residual(self.handle, which))
+
+    def eval_jacobian(self, which=0):
+        _lib.check(self.L.rst_b200_eval_jacobian(self.handle, which))
+
+    def solve(self):
+        _lib.check(self.L.rst_b200_solve(self.handle))
+
+    def reduce(self, which=0):
+        sc = _lib.Scalars()
+        _lib.check(self.L.rst_b200_reduce(self.handle, which, C.byref(sc)))
+        return sc
+
+    def sync(self):
+        _lib.check(self.L.rst_b200_sync(self.handle))
+
+    def launch_count(self):
+        return int(self.L.rst_b200_launch_count(self.handle))
+
+    def set_allgather(self, fn):
+        """fn(d_send_ptr, d_recv_ptr, doubles_per_rank, stream_ptr) -> 0 on success."""
+        def tramp(ctx, send, recv, count, stream):
+            try:
+                return int(fn(send, recv, count, stream) or 0)
+            except Exception:  # never let an exception cross the C ABI
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._allgather_cb = _lib.ALLGATHER_FN(tramp)
+        _lib.check(self.L.rst_b200_set_allgather(self.handle, self._allgather_cb, None))

@@ -1,0 +1,106 @@
+"""CPU-side checks of the product's host logic: the CUDA-C emitter, the built library's exported ABI and
+the loud failure without a GPU.  No compute calls are made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import sympy as sp
+
+from oracle import oracle as orc
+from rustedscithe_b200 import build as rbuild
+from rustedscithe_b200 import lib as rlib
+from rustedscithe_b200 import problems
+from rustedscithe_b200.emit.cuda_emitter import emit_problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    return rbuild.build()
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "rst_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rst_b200_\w+|rustedscithe_aot_\w+)\s*\(", hdr))
+    declared -= {"rst_b200_allgather_fn"}
+    assert declared == set(rlib.SYMBOLS), declared ^ set(rlib.SYMBOLS)
+    L = rlib.load()
+    for name in declared:
+        assert hasattr(L, name)
+    assert L.rst_b200_version() == 1
+
+
+def test_problem_registry_matches_catalogue(built):
+    L = rlib.load()
+    keys = [L.rst_b200_problem_key(i).decode() for i in range(L.rst_b200_problem_count())]
+    assert keys == rbuild.BUILTIN_PROBLEMS
+    for k in keys:
+        nv, npar, h = C.c_int(), C.c_int(), C.c_char_p()
+        assert L.rst_b200_problem_info(k.encode(), C.byref(nv), C.byref(npar), C.byref(h)) == 0
+        spec = problems.get(k)
+        assert (nv.value, npar.value) == (spec.nv, len(spec.params))
+        assert h.value.decode() == emit_problem(spec).problem_hash
+
+
+def test_create_fails_loudly_without_gpu(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from rustedscithe_b200.solver import NRBVP
+    with pytest.raises(rlib.RstB200Error) as e:
+        NRBVP("linear2", None, 100)
+    assert e.value.code == rlib.ERR_CUDA
+
+
+def test_create_validates_arguments_before_touching_the_device(built):
+    from rustedscithe_b200.solver import NRBVP
+    with pytest.raises(rlib.RstB200Error) as e:   # numeric_discretization.rs:60-67
+        NRBVP("linear2", None, 100, boundary_conditions={"y": [(0, 0.0)]})
+    assert e.value.code == rlib.ERR_INVALID and "boundary conditions" in str(e.value)
+    with pytest.raises(rlib.RstB200Error) as e:   # :156-158
+        NRBVP("linear2", None, 1)
+    assert e.value.code == rlib.ERR_INVALID
+    with pytest.raises(KeyError):
+        NRBVP("no_such_problem", None, 10)
+
+
+@pytest.mark.parametrize("key", ["linear2", "damp1", "damp1p", "combustion6", "flame12", "coupled8"])
+def test_emitted_expressions_match_sympy_and_the_hand_written_oracle(key):
+    """The emitter's pruned df/dy pattern and values agree with (a) direct sympy evaluation of the spec and
+    (b) the independently hand-written C right-hand sides of the oracle."""
+    spec = problems.get(key)
+    em = emit_problem(spec)
+    nv = spec.nv
+    ys = [sp.Symbol(n, real=True) for n in spec.names]
+    ps = [sp.Symbol(n, real=True) for n in spec.params]
+    x = sp.Symbol(spec.arg, real=True)
+    eqs = [sp.sympify(e) for e in spec.rhs()]
+    rng = np.random.default_rng(3)
+    yv = 0.3 + 0.5 * rng.random(nv)
+    pv = list(spec.param_values)
+    subs = dict(zip(ys, yv)) | dict(zip(ps, pv)) | {x: 0.37}
+    f_sym = np.array([float(e.evalf(30, subs=subs)) for e in eqs])
+    J_sym = np.array([[float(sp.diff(e, y).evalf(30, subs=subs)) for y in ys] for e in eqs])
+    f_orc, J_orc = orc.problem_rhs(key, 0.37, yv, pv or None)
+    assert np.max(np.abs(f_sym - f_orc) / np.maximum(1e-300, np.abs(f_sym) + 1e-12 * np.max(np.abs(f_sym)))) < 1e-12
+    assert np.max(np.abs(J_sym - J_orc) / (np.abs(J_sym) + 1e-12 * np.max(np.abs(J_sym)) + 1e-300)) < 1e-12
+    assert np.array_equal(np.array(em.pattern).reshape(nv, nv) != 0, J_orc != 0.0)
+    assert np.array_equal(orc.problem_pattern(key), np.array(em.pattern, dtype=np.uint8).reshape(nv, nv))
+
+
+def test_emitter_rejects_functions_outside_the_reference_opcode_set():
+    spec = problems.get("damp1")
+    bad = problems.ProblemSpec(key="bad", names=spec.names, rhs=lambda: [sp.gamma(sp.Symbol("z", real=True)), sp.Float(0)],
+                               bcs=spec.bcs, bounds=spec.bounds, rtol=spec.rtol, guess=spec.guess)
+    with pytest.raises(ValueError, match="opcode"):
+        emit_problem(bad)
+
+
+def test_emitted_literals_round_trip_exactly():
+    em = emit_problem(problems.get("combustion6"))
+    for lit in re.findall(r"[-+]?\d\.\d{17}e[-+]\d{2}", em.source):
+        assert float("%.17e" % float(lit)) == float(lit)

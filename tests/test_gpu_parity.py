@@ -1,0 +1,330 @@
+"""GPU parity tests: the CUDA path (through the C ABI, librst_b200.so) against the CPU oracle on the same
+seeded inputs.  Tolerances are BASELINE.json's: residual / Jacobian entries 1e-12 relative, each linear-solve
+dy 1e-10 relative to the reference banded LU, converged solutions 1e-9 with the same Newton iteration count."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from rustedscithe_b200 import build as rbuild
+from rustedscithe_b200 import problems
+from rustedscithe_b200.solver import NRBVP, DampedSolverOptions
+
+pytestmark = pytest.mark.gpu
+
+TOL_FJ = 1e-12      # per-entry residual / Jacobian, relative
+TOL_DY = 1e-10      # linear solve, relative to the oracle's banded LU
+TOL_SOL = 1e-9      # converged solution
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    rbuild.build()
+
+
+def _oracle(key, n_steps, scheme="forward", params=None, **kw):
+    spec = problems.get(key)
+    return orc.OracleBVP(key, n_steps, spec.bc_list(), t0=spec.t0, t_end=spec.t_end, scheme=scheme,
+                         params=params if params is not None else (spec.param_values or None), **kw)
+
+
+def _gpu(key, n_steps, scheme="forward", slab=0, guess=None, **kw):
+    spec = problems.get(key)
+    opts = DampedSolverOptions.from_spec(spec, scheme=scheme, slab=slab)
+    return NRBVP(key, guess, n_steps, opts, **kw)
+
+
+def _rel(a, b, floor=1.0):
+    return np.max(np.abs(a - b) / np.maximum(floor, np.abs(b)))
+
+
+CASES = [("linear2", 1000), ("damp1", 128), ("damp1p", 77), ("combustion6", 300), ("flame12", 257), ("coupled8", 100)]
+
+
+@pytest.mark.parametrize("key,n_steps", CASES)
+@pytest.mark.parametrize("scheme", ["forward", "trapezoid"])
+def test_residual_and_jacobian_values_match_oracle(key, n_steps, scheme):
+    """a1/a2 through the reference's own AOT ABI (host pointers, args = [params..., y_reduced...])."""
+    rng = np.random.default_rng(11)
+    o = _oracle(key, n_steps, scheme)
+    g = _gpu(key, n_steps, scheme)
+    y = 0.35 + 0.6 * rng.random(o.n)
+    r_gpu, r_ref = g.fun_call(y), o.residual(y)
+    # residual rows are differences of O(1) terms: relative to max(1, |ref|)
+    assert _rel(r_gpu, r_ref) < TOL_FJ
+    rows, cols, doff, dpos, kl, ku = g.jacobian_structure()
+    orows, ocols, odoff, odpos, okl, oku = o.structure()
+    assert np.array_equal(rows, orows) and np.array_equal(cols, ocols)
+    assert np.array_equal(doff, odoff) and np.array_equal(dpos, odpos) and (kl, ku) == (okl, oku)
+    v_gpu, v_ref = g.jac_call(y), o.jacobian_values(y)
+    assert np.max(np.abs(v_gpu - v_ref) / np.maximum(np.abs(v_ref), 1e-300 + 1e-12 * np.max(np.abs(v_ref)))) < 50 * TOL_FJ
+    assert _rel(v_gpu, v_ref) < TOL_FJ
+    g.close()
+
+
+def test_aot_abi_error_behaviour():
+    """codegen_c_aot_library.rs:382-384: 0 on NULL pointers or length mismatch."""
+    import ctypes as C
+    g = _gpu("linear2", 16)
+    L = g.L
+    L.rst_b200_aot_bind(g.handle)
+    args, out = np.zeros(32), np.zeros(32)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    assert L.rustedscithe_aot_eval_residual(p(args), 32, p(out), 32) == 1
+    assert L.rustedscithe_aot_eval_residual(p(args), 31, p(out), 32) == 0
+    assert L.rustedscithe_aot_eval_residual(p(args), 32, p(out), 31) == 0
+    assert L.rustedscithe_aot_eval_residual(None, 32, p(out), 32) == 0
+    assert L.rustedscithe_aot_eval_jacobian_values(p(args), 32, p(out), 5) == 0
+    g.close()
+
+
+def test_nonuniform_mesh_and_parameters():
+    n = 90
+    rng = np.random.default_rng(5)
+    mesh = np.concatenate([[0.0], np.sort(rng.random(n - 1)), [1.0]])
+    spec = problems.get("damp1p")
+    o = orc.OracleBVP("damp1p", n, spec.bc_list(), mesh=mesh, params=[1.3, -0.4])
+    g = NRBVP("damp1p", None, n, mesh=mesh, params=[1.3, -0.4])
+    y = 0.2 + rng.random(o.n)
+    assert _rel(g.fun_call(y), o.residual(y)) < TOL_FJ
+    assert _rel(g.jac_call(y), o.jacobian_values(y)) < TOL_FJ
+    # parameter re-binding through the args prefix (generated_solver_handoff.rs:4017)
+    o2 = orc.OracleBVP("damp1p", n, spec.bc_list(), mesh=mesh, params=[0.1, 2.0])
+    assert _rel(g.fun_call(y, params=[0.1, 2.0]), o2.residual(y)) < TOL_FJ
+    g.close()
+
+
+SOLVE_CASES = [
+    ("linear2", 1000, 0), ("linear2", 37, 4), ("linear2", 2, 0), ("linear2", 3, 2), ("damp1", 128, 8),
+    ("combustion6", 1000, 0), ("combustion6", 333, 5), ("flame12", 500, 0), ("flame12", 2000, 32),
+    ("flame12", 65, 64), ("coupled8", 200, 3),
+]
+
+
+@pytest.mark.parametrize("key,n_steps,slab", SOLVE_CASES)
+@pytest.mark.parametrize("scheme", ["forward", "trapezoid"])
+def test_linear_solve_matches_faithful_banded_lu(key, n_steps, slab, scheme):
+    """a3-a5/a7: DirectLinearSolver::solve_in_place drop-in vs BandedAssembly -> Banded -> AB -> DGBTF2 -> DGBTRS."""
+    rng = np.random.default_rng(23)
+    spec = problems.get(key)
+    o = _oracle(key, n_steps, scheme)
+    g = _gpu(key, n_steps, scheme, slab=slab)
+    y = spec.guess(n_steps) * (1.0 + 0.01 * rng.standard_normal(o.n))
+    vals = o.jacobian_values(y)
+    rhs = o.residual(y)
+    dy_ref = o.solve_banded(vals, rhs)
+    g.set_state(y)
+    g.eval_jacobian()
+    g.factor()
+    dy = g.solve_in_place(rhs)
+    err = np.linalg.norm(dy - dy_ref) / np.linalg.norm(dy_ref)
+    assert err < TOL_DY, err
+    # multi-RHS, column-major with ldb > n (solver_traits.rs:9-14)
+    ldb = o.n + 3
+    buf = np.zeros(2 * ldb)
+    rhs2 = np.cos(np.arange(o.n))
+    buf[:o.n], buf[ldb:ldb + o.n] = rhs, rhs2
+    out = g.solve_multiple_in_place(buf, 2, ldb)
+    assert np.linalg.norm(out[:o.n] - dy_ref) / np.linalg.norm(dy_ref) < TOL_DY
+    ref2 = o.solve_banded(vals, rhs2)
+    assert np.linalg.norm(out[ldb:ldb + o.n] - ref2) / np.linalg.norm(ref2) < TOL_DY
+    g.close()
+
+
+def test_solver_error_behaviour():
+    from rustedscithe_b200 import lib as rlib
+    g = _gpu("linear2", 64)
+    with pytest.raises(rlib.RstB200Error) as e:      # BandedError::NotFactorized
+        g.solve_in_place(np.zeros(128))
+    assert e.value.code == rlib.ERR_NOT_FACTORIZED
+    g.set_state(np.zeros(128))
+    g.eval_jacobian()
+    g.factor()
+    with pytest.raises(rlib.RstB200Error) as e:      # BandedError::DimensionMismatch
+        g.solve_in_place(np.zeros(127))
+    assert e.value.code == rlib.ERR_INVALID
+    g.close()
+
+
+def test_singular_system_reports_zero_pivot():
+    """Two conditions on y and none on z for y' = z, z' = 0 is fine; pinning z twice leaves y undetermined."""
+    from rustedscithe_b200 import lib as rlib
+    g = NRBVP("linear2", None, 32, boundary_conditions={"z": [(0, 1.0), (1, 1.0)]})
+    g.set_state(np.zeros(64))
+    g.eval_jacobian()
+    g.factor()
+    with pytest.raises(rlib.RstB200Error) as e:
+        g.solve_in_place(np.ones(64))
+    assert e.value.code == rlib.ERR_ZERO_PIVOT
+    g.close()
+
+
+NEWTON_CASES = [("linear2", 80), ("linear2", 1000), ("damp1", 64), ("combustion6", 1000), ("flame12", 400),
+                ("coupled8", 150)]
+
+
+@pytest.mark.parametrize("key,n_steps", NEWTON_CASES)
+def test_newton_matches_oracle_iteration_counts_and_solution(key, n_steps):
+    """a8-a11: same counters (iterations / linear systems / Jacobians) and converged solution within 1e-9."""
+    spec = problems.get(key)
+    o = _oracle(key, n_steps)
+    lo, hi = spec.bounds_per_var()
+    ref = o.newton(spec.guess(n_steps), o.per_unknown(lo), o.per_unknown(hi), o.per_unknown(spec.rtol_per_var()),
+                   abs_tol=spec.abs_tol, max_iterations=spec.max_iterations, max_jac=spec.max_jac,
+                   max_damp_iter=spec.max_damp_iter, damp_factor=spec.damp_factor)
+    g = _gpu(key, n_steps, guess=spec.guess(n_steps))
+    sol = g.try_solve()
+    st = g.get_statistics()
+    assert st["status"] == ref.status == 1
+    assert (st["number of iterations"], st["number of solving linear systems"],
+            st["number of jacobians recalculations"]) == (ref.iterations, ref.linear_solves, ref.jac_recalcs)
+    assert st["factorizations"] == ref.jac_recalcs          # factors are cached, the reference refactors per solve
+    assert np.max(np.abs(sol - ref.y) / np.maximum(1.0, np.abs(ref.y))) < TOL_SOL
+    full = g.get_result()
+    assert np.max(np.abs(full - o.full_solution(ref.y)) / np.maximum(1.0, np.abs(o.full_solution(ref.y)))) < TOL_SOL
+    g.close()
+
+
+def test_config_c1_closed_form():
+    """examples/bvp_damped_aot_guide.rs:84-109 at N = 1000: max |y - x| < 5e-5."""
+    spec = problems.get("linear2")
+    g = _gpu("linear2", 1000, guess=spec.guess(1000))
+    assert g.try_solve() is not None
+    full = g.get_result()
+    x = np.linspace(0.0, 1.0, 1001)
+    assert np.max(np.abs(full[:, 0] - x)) < 5e-5 and np.max(np.abs(full[:, 1] - 1.0)) < 5e-5
+    g.close()
+
+
+def test_bound_violation_status_matches_oracle():
+    """status -3 path (BVP_utils_damped.rs:39-61, NR_Damp_solver_damped.rs:1898-1905)."""
+    spec = problems.get("linear2")
+    n = 50
+    o = _oracle("linear2", n)
+    y0 = spec.guess(n)
+    y0[1::2] = 1.2          # y components sit on the upper bound and the first step points outward
+    lo, hi = spec.bounds_per_var()
+    ref = o.newton(y0, o.per_unknown(lo), o.per_unknown(hi), o.per_unknown(spec.rtol_per_var()), abs_tol=spec.abs_tol,
+                   max_iterations=spec.max_iterations)
+    g = _gpu("linear2", n, guess=y0)
+    g.try_solve()
+    st = g.get_statistics()
+    assert st["status"] == ref.status
+    assert st["number of iterations"] == ref.iterations
+    g.close()
+
+
+# ---- BASELINE.json full sizes: size-independent properties ------------------------------------------
+def test_config_c2_million_points_closed_form_and_idempotence():
+    """C2: 2-variable BVP at 10^6 points.  The discrete solution of y'=z, z'=0, y(0)=0, z(1)=1 is y = x, z = 1
+    on any mesh; a second solve from the converged state must converge in one iteration without moving."""
+    n = 1_000_000
+    spec = problems.get("linear2")
+    g = _gpu("linear2", n, guess=spec.guess(n))
+    sol = g.try_solve()
+    assert sol is not None
+    full = g.get_result()
+    x = np.arange(n + 1) / n
+    assert np.max(np.abs(full[:, 0] - x)) < 1e-9 and np.max(np.abs(full[:, 1] - 1.0)) < 1e-9
+    g2 = _gpu("linear2", n, guess=sol)
+    sol2 = g2.try_solve()
+    assert g2.get_statistics()["number of iterations"] == 1
+    assert np.max(np.abs(sol2 - sol)) < 1e-9
+    g.close(); g2.close()
+
+
+def test_config_c3_million_points_newton_converges_and_residual_vanishes():
+    """C3: flame12 at 10^6 points.  Newton must converge in the same number of iterations as the oracle does on a
+    coarse mesh (mesh-independent convergence), the converged residual must be at rounding level, and the linear
+    solve must satisfy J dy = F (checked through the damped loop: a Newton step from the solution is ~0)."""
+    n = 1_000_000
+    spec = problems.get("flame12")
+    o = _oracle("flame12", 2000)
+    lo, hi = spec.bounds_per_var()
+    ref = o.newton(spec.guess(2000), o.per_unknown(lo), o.per_unknown(hi), o.per_unknown(spec.rtol_per_var()),
+                   abs_tol=spec.abs_tol, max_iterations=spec.max_iterations, max_jac=spec.max_jac,
+                   max_damp_iter=spec.max_damp_iter, damp_factor=spec.damp_factor)
+    g = _gpu("flame12", n, guess=spec.guess(n))
+    sol = g.try_solve()
+    st = g.get_statistics()
+    assert sol is not None and st["status"] == 1
+    assert st["number of iterations"] == ref.iterations
+    r = g.fun_call(sol)
+    assert np.linalg.norm(r) < 1e-6
+    # coarse-vs-fine agreement of the profiles at shared nodes (first-order scheme: O(h) apart)
+    fine = g.get_result()[:: n // 2000]
+    coarse = o.full_solution(ref.y)
+    assert np.max(np.abs(fine - coarse) / np.maximum(1.0, np.abs(coarse))) < 5e-2
+    g.close()
+
+
+# ---- multi-rank path, emulated in one process through the phase-split ABI --------------------------------
+@pytest.mark.parametrize("key,n_steps,world", [("linear2", 101, 2), ("flame12", 300, 3), ("combustion6", 64, 4)])
+def test_emulated_mesh_slab_ranks_match_single_rank(key, n_steps, world):
+    import ctypes as C
+    spec = problems.get(key)
+    rng = np.random.default_rng(1)
+    nv = spec.nv
+    y = spec.guess(n_steps) * (1.0 + 0.01 * rng.standard_normal(nv * n_steps))
+    single = _gpu(key, n_steps)
+    single.set_state(y)
+    single.eval_jacobian()
+    single.factor()
+    single.solve()
+    sc1 = single.reduce(0)
+    ranks = [NRBVP(key, None, n_steps, DampedSolverOptions.from_spec(spec, rank=r, world=world)) for r in range(world)]
+    L = single.L
+
+    def gather(which_send, which_recv, count):
+        for dst in ranks:
+            for r, src in enumerate(ranks):
+                nbytes = count * 8
+                a = src.device_ptr(which_send)
+                b = dst.device_ptr(which_recv) + r * nbytes
+                _memcpy_d2d(b, a, nbytes)
+
+    for rk in ranks:
+        rk.set_state(y)
+        rk.eval_jacobian()
+        assert L.rst_b200_factor_local(rk.handle) == 0
+        rk.sync()
+    gather(6, 8, 2 * nv * nv)
+    for rk in ranks:
+        assert L.rst_b200_factor_reduced(rk.handle) == 0
+        assert L.rst_b200_solve_local_forward(rk.handle) == 0
+        rk.sync()
+    gather(7, 9, nv)
+    for rk in ranks:
+        assert L.rst_b200_solve_reduced_backward(rk.handle) == 0
+        assert L.rst_b200_reduce_local(rk.handle, 0) == 0
+        rk.sync()
+    gather(10, 11, 8)
+    from rustedscithe_b200 import lib as rlib
+    dy_single = _read(single.device_ptr(4), (n_steps + 1) * nv)
+    for rk in ranks:
+        b, e = C.c_int64(), C.c_int64()
+        L.rst_b200_dist_range(rk.handle, C.byref(b), C.byref(e))
+        dy = _read(rk.device_ptr(4), (e.value - b.value + 1) * nv)
+        ref = dy_single[b.value * nv:(e.value + 1) * nv]
+        assert np.linalg.norm(dy - ref) <= 1e-10 * np.linalg.norm(dy_single)
+        sc = rlib.Scalars()
+        assert L.rst_b200_reduce_finish(rk.handle, C.byref(sc)) == 0
+        assert abs(sc.sumsq_step - sc1.sumsq_step) <= 1e-10 * sc1.sumsq_step
+        assert abs(sc.tol_sum - sc1.tol_sum) <= 1e-12 * sc1.tol_sum
+        assert sc.fbound == pytest.approx(sc1.fbound, rel=1e-9)
+    for rk in ranks:
+        rk.close()
+    single.close()
+
+
+def _memcpy_d2d(dst, src, nbytes):
+    import ctypes as C
+    from rustedscithe_b200 import lib as rlib
+    assert rlib.load().rst_b200_memcpy(C.c_void_p(dst), C.c_void_p(src), nbytes, 3) == 0
+
+
+def _read(ptr, count):
+    import ctypes as C
+    from rustedscithe_b200 import lib as rlib
+    out = np.zeros(count)
+    assert rlib.load().rst_b200_memcpy(out.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), count * 8, 2) == 0
+    return out

@@ -129,6 +129,8 @@ int rst_b200_reduce(rst_b200_solver *s, int which_state, rst_b200_scalars *out);
 int rst_b200_make_trial(rst_b200_solver *s, double lambda);
 /* accept the trial state as the current state */
 int rst_b200_accept_trial(rst_b200_solver *s);
+/* device-side checkpoint of the state: restore == 0 saves Y, restore != 0 copies it back (no host traffic) */
+int rst_b200_checkpoint(rst_b200_solver *s, int restore);
 
 /* whole damped Newton loop (try_main_loop_damped, NR_Damp_solver_damped.rs:2027-2156) */
 int rst_b200_newton_solve(rst_b200_solver *s, const rst_b200_newton_opts *opts, rst_b200_newton_stats *stats);

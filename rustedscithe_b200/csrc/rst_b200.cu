@@ -153,6 +153,7 @@ struct rst_b200_solver {
     // device buffers
     double *Y = nullptr, *Yt = nullptr, *F = nullptr, *A = nullptr, *B = nullptr, *dY = nullptr;
     double *d_mesh = nullptr, *d_params = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_rtol = nullptr;
+    double *Ysave = nullptr;  // device-side checkpoint of Y (rst_b200_checkpoint)
     double *d_tmp = nullptr;  // [n*nv + nv] staging for reduced-order host drop-ins
     std::vector<void *> owned;
     std::vector<LevelBuf> levels;      // local condensation levels
@@ -767,6 +768,19 @@ extern "C" int rst_b200_make_trial(rst_b200_solver *s, double lambda) {
 extern "C" int rst_b200_accept_trial(rst_b200_solver *s) {
     if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
     std::swap(s->Y, s->Yt);
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_checkpoint(rst_b200_solver *s, int restore) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    const size_t bytes = (size_t)(s->n + 1) * s->nv * sizeof(double);
+    if (!s->Ysave) TRY(dev_alloc(s, &s->Ysave, (size_t)(s->n + 1) * s->nv));
+    if (restore) {
+        CUDA_TRY(cudaMemcpyAsync(s->Y, s->Ysave, bytes, cudaMemcpyDeviceToDevice, s->stream));
+        s->have_jac = s->factored = false;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(s->Ysave, s->Y, bytes, cudaMemcpyDeviceToDevice, s->stream));
+    }
     return RST_B200_OK;
 }
 

@@ -75,6 +75,7 @@ SYMBOLS = {
     "rst_b200_reduce": (C.c_int, [_H, C.c_int, C.POINTER(Scalars)]),
     "rst_b200_make_trial": (C.c_int, [_H, C.c_double]),
     "rst_b200_accept_trial": (C.c_int, [_H]),
+    "rst_b200_checkpoint": (C.c_int, [_H, C.c_int]),
     "rst_b200_newton_solve": (C.c_int, [_H, C.POINTER(NewtonOpts), C.POINTER(NewtonStats)]),
     "rst_b200_newton_iterate": (C.c_int, [_H, C.POINTER(NewtonOpts), C.c_int, C.POINTER(NewtonStats)]),
     "rst_b200_solve_in_place": (C.c_int, [_H, c_f64_p, C.c_size_t]),

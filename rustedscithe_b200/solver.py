@@ -243,6 +243,9 @@ class NRBVP:
         _lib.check(self.L.rst_b200_reduce(self.handle, which, C.byref(sc)))
         return sc
 
+    def checkpoint(self, restore=False):
+        _lib.check(self.L.rst_b200_checkpoint(self.handle, 1 if restore else 0))
+
     def sync(self):
         _lib.check(self.L.rst_b200_sync(self.handle))
 

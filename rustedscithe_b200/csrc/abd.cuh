@@ -55,8 +55,8 @@ __device__ __forceinline__ int rank_in(unsigned gbits, int r) { return __popc(gb
 
 template <int G>
 __device__ __forceinline__ unsigned group_bits(unsigned ballot, int gw) {
-    if (G == 32) return ballot;
-    return (ballot >> (gw * G)) & ((1u << G) - 1u);
+    if constexpr (G == 32) return ballot;
+    else return (ballot >> (gw * G)) & ((1u << G) - 1u);
 }
 
 // arg-max of |v| over the lanes of a group that are still candidates; returns the group-relative lane.

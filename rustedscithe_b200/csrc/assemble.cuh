@@ -116,4 +116,83 @@ __global__ void __launch_bounds__(128) assemble_kernel(AsmArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused F + J assembly with shared-memory staged block stores (nv >= 6).
+// In assemble_kernel every thread streams its own nv*nv block (1152 B at nv = 12) with 16-byte stores, i.e. a
+// warp store instruction touches 32 different 128-byte lines with half a sector each (measured 18 % of the HBM
+// roofline at nv = 12, profiles/r01_a_summary.md).  Here one warp owns 32 consecutive intervals = ONE contiguous
+// 32*nv*nv*8-byte region of A: each lane stages its block into a padded (odd pitch -> conflict-free) shared tile,
+// then the warp streams the tile out with fully coalesced 512-byte store instructions.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void stage_block(double *tile_row, const double *fy, double hs, double idsign) {
+#pragma unroll
+    for (int e = 0; e < NV * NV; ++e) tile_row[e] = fma(-hs, fy[e], ((e / NV) == (e % NV)) ? idsign : 0.0);
+}
+
+template <int NV>
+__device__ __forceinline__ void flush_tile(const double *tile, double *dst, int nvalid, int lane) {
+    constexpr int BL = NV * NV, PITCH = BL | 1;
+    static_assert(BL % 2 == 0, "staged assembly needs an even block size");
+    double2 *d2 = reinterpret_cast<double2 *>(dst);
+    const int total2 = nvalid * (BL / 2);
+#pragma unroll 4
+    for (int q2 = lane; q2 < total2; q2 += 32) {
+        const int jj = q2 / (BL / 2);
+        const int e = 2 * (q2 - jj * (BL / 2));
+        const double *s = tile + jj * PITCH + e;
+        st_cs2(d2 + q2, make_double2(s[0], s[1]));
+    }
+}
+
+template <class P, bool TRAPEZOID>
+__global__ void __launch_bounds__(32) assemble_j_staged_kernel(AsmArgs a) {
+    constexpr int NV = P::NV, BL = NV * NV, PITCH = BL | 1;
+    __shared__ double tile[32 * PITCH];
+    const int lane = threadIdx.x;
+    const int64_t j0 = (int64_t)blockIdx.x * 32;
+    const int64_t j = j0 + lane;
+    const bool valid = j < a.n;
+    const int nvalid = (int)((a.n - j0) < 32 ? (a.n - j0) : 32);
+    double y0[NV], y1[NV], f0[NV], f1[NV];
+    double t = 0.0, t1 = 0.0, h = a.h;
+    if (valid) {
+        load_node<NV>(a.Y + j * NV, y0);
+        load_node<NV>(a.Y + (j + 1) * NV, y1);
+        if (a.mesh) {
+            t = a.mesh[j];
+            t1 = a.mesh[j + 1];
+            h = t1 - t;
+        } else {
+            t = a.t0 + (double)(j + a.j_offset) * a.h;
+            t1 = a.t0 + (double)(j + a.j_offset + 1) * a.h;
+        }
+        double fy[BL];
+        P::eval_f_fy(t, y0, a.params, f0, fy);
+        stage_block<NV>(tile + lane * PITCH, fy, TRAPEZOID ? 0.5 * h : h, -1.0);
+    }
+    __syncwarp();
+    flush_tile<NV>(tile, a.A + j0 * (int64_t)BL, nvalid, lane);
+    if constexpr (TRAPEZOID) {
+        __syncwarp();
+        if (valid) {
+            double fy[BL];
+            P::eval_f_fy(a.trap_time ? t1 : t, y1, a.params, f1, fy);
+            stage_block<NV>(tile + lane * PITCH, fy, 0.5 * h, 1.0);
+        }
+        __syncwarp();
+        flush_tile<NV>(tile, a.B + j0 * (int64_t)BL, nvalid, lane);
+    }
+    if (valid) {
+        double *r = a.F + j * NV;
+        if constexpr (TRAPEZOID) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) r[i] = y1[i] - y0[i] - 0.5 * h * (f0[i] + f1[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) r[i] = y1[i] - y0[i] - h * f0[i];
+        }
+    }
+}
+
 }  // namespace rst

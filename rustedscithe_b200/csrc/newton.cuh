@@ -40,24 +40,42 @@ __device__ __forceinline__ double warp_min(double v) {
 }
 
 // one pass over the step: all scalars a damping trial needs
+template <int NV>
 __global__ void __launch_bounds__(256) newton_reduce_kernel(ReduceArgs a) {
-    const int64_t total = a.n_nodes * a.nv;
     double ss = 0.0, tol = 0.0, fb = 1.0, nanf = 0.0;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t node = idx / a.nv;
-        const int v = (int)(idx - node * a.nv);
-        const bool pinned = (a.has_left && node == 0 && ((a.left_mask >> v) & 1ull)) ||
-                            (a.has_right && node == a.n_nodes - 1 && ((a.right_mask >> v) & 1ull));
-        const double s = a.dY[idx];
-        if (s != s) nanf = 2.0;
-        if (pinned) continue;
-        const double y = a.Y[idx];
-        ss = fma(s, s, ss);
-        tol = fma(fabs(y), a.rtol[v], tol);
-        const double nv_ = y + s;  // the reference evaluates y + step although it applies y - lambda*step
-        if (nv_ > a.hi[v]) fb = fmax(fmin(fb, (a.hi[v] - y) / (nv_ - y)), 0.0);
-        else if (nv_ < a.lo[v]) fb = fmin(fb, (y - a.lo[v]) / (y - nv_));
+    double lo[NV], hi[NV], rt[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { lo[v] = a.lo[v]; hi[v] = a.hi[v]; rt[v] = a.rtol[v]; }
+    // one thread per node: nv contiguous doubles of y and of the step (vectorised), no index division
+    for (int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; node < a.n_nodes;
+         node += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long pinmask = 0ull;
+        if (a.has_left && node == 0) pinmask |= a.left_mask;
+        if (a.has_right && node == a.n_nodes - 1) pinmask |= a.right_mask;
+        double yv[NV], sv[NV];
+        if constexpr (NV % 2 == 0) {
+            const double2 *y2 = reinterpret_cast<const double2 *>(a.Y + node * NV);
+            const double2 *s2 = reinterpret_cast<const double2 *>(a.dY + node * NV);
+#pragma unroll
+            for (int v = 0; v < NV; v += 2) {
+                const double2 p = y2[v >> 1], q = s2[v >> 1];
+                yv[v] = p.x; yv[v + 1] = p.y; sv[v] = q.x; sv[v + 1] = q.y;
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) { yv[v] = a.Y[node * NV + v]; sv[v] = a.dY[node * NV + v]; }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const double s = sv[v], y = yv[v];
+            if (s != s) nanf = 2.0;
+            if ((pinmask >> v) & 1ull) continue;
+            ss = fma(s, s, ss);
+            tol = fma(fabs(y), rt[v], tol);
+            const double nv_ = y + s;  // the reference evaluates y + step although it applies y - lambda*step
+            if (nv_ > hi[v]) fb = fmax(fmin(fb, (hi[v] - y) / (nv_ - y)), 0.0);
+            else if (nv_ < lo[v]) fb = fmin(fb, (y - lo[v]) / (y - nv_));
+        }
     }
     if (a.F) {
         const int64_t nf = a.n_rows * a.nv;

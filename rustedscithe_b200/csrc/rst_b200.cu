@@ -10,11 +10,15 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "abd.cuh"
+#include "abd2.cuh"
+#include "abd3.cuh"
+#include "tps.cuh"
 #include "assemble.cuh"
 #include "newton.cuh"
 #include "generated/generated_problems.cuh"
@@ -49,6 +53,16 @@ static void launch_assemble(const AsmArgs &a, bool with_j, bool trap, cudaStream
     const int threads = 128;
     const unsigned blocks = (unsigned)((a.n + threads - 1) / threads);
     if (blocks == 0) return;
+    // nv >= 6: blocks of A are staged through shared memory and streamed out coalesced (assemble.cuh)
+    if constexpr (P::NV >= 6 && (P::NV % 2 == 0) && (32 * ((P::NV * P::NV) | 1) * 8 <= 48 * 1024)) {
+        static const bool direct = std::getenv("RST_B200_ASSEMBLE_DIRECT") != nullptr;
+        if (with_j && !direct) {
+            const unsigned wblocks = (unsigned)((a.n + 31) / 32);
+            if (trap) assemble_j_staged_kernel<P, true><<<wblocks, 32, 0, st>>>(a);
+            else assemble_j_staged_kernel<P, false><<<wblocks, 32, 0, st>>>(a);
+            return;
+        }
+    }
     if (!trap) {
         if (with_j) assemble_kernel<P, true, false><<<blocks, threads, 0, st>>>(a);
         else assemble_kernel<P, false, false><<<blocks, threads, 0, st>>>(a);
@@ -84,7 +98,20 @@ struct SolverVT {
                 unsigned long long rm, unsigned *flags, cudaStream_t);
     void (*residual)(const double *A, const double *B, const double *X, const double *rhs, double *out, int64_t n,
                      cudaStream_t);
+    void (*reduce)(const ReduceArgs &, int blocks, cudaStream_t);
 };
+
+// kernel generation: "v1" = one panel row per lane + shuffle broadcast (abd.cuh), default "v2" = two rows per lane +
+// shared-memory broadcast (abd2.cuh).  Factor and forward kernels of one generation share the factor layout.
+static int kernel_generation() {
+    static int gen = [] {
+        const char *e = std::getenv("RST_B200_KERNELS");
+        if (e && std::strcmp(e, "v1") == 0) return 1;
+        if (e && std::strcmp(e, "v2") == 0) return 2;
+        return 3;  // abd3.cuh: one row per lane, REDUX pivot search, shared-memory broadcast, reciprocal multipliers
+    }();
+    return gen;
+}
 
 template <int NV>
 struct SolverImpl {
@@ -94,11 +121,32 @@ struct SolverImpl {
         return (unsigned)((nslabs + per_block - 1) / per_block);
     }
     static void factor(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
+        if constexpr (NV % 2 == 0) {
+            if (kernel_generation() == 2) {
+                const unsigned blocks = grid_for(L.nslabs, NV);
+                if (ident_b) abd_factor2_kernel<NV, true><<<blocks, 128, 0, st>>>(L, flags);
+                else abd_factor2_kernel<NV, false><<<blocks, 128, 0, st>>>(L, flags);
+                return;
+            }
+            // REDUX with several sub-warp masks serialises per mask: generation 3 only where a slab spans >= 16 lanes
+            if (kernel_generation() == 3 && NV >= 6) {
+                const unsigned blocks = grid_for(L.nslabs, 2 * NV);
+                if (ident_b) abd_factor3_kernel<NV, true><<<blocks, 128, 0, st>>>(L, flags);
+                else abd_factor3_kernel<NV, false><<<blocks, 128, 0, st>>>(L, flags);
+                return;
+            }
+        }
         const unsigned blocks = grid_for(L.nslabs, 2 * NV);
         if (ident_b) abd_factor_kernel<NV, true><<<blocks, 128, 0, st>>>(L, flags);
         else abd_factor_kernel<NV, false><<<blocks, 128, 0, st>>>(L, flags);
     }
     static void forward(const AbdLevel &L, cudaStream_t st) {
+        if constexpr (NV % 2 == 0) {
+            if (kernel_generation() == 2) {
+                abd_forward2_kernel<NV><<<grid_for(L.nslabs, NV), 128, 0, st>>>(L);
+                return;
+            }
+        }
         abd_forward_kernel<NV><<<grid_for(L.nslabs, 2 * NV), 128, 0, st>>>(L);
     }
     static void backward(const AbdLevel &L, cudaStream_t st) {
@@ -113,7 +161,10 @@ struct SolverImpl {
         const int64_t total = n * NV;
         block_residual_kernel<NV><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(A, B, X, rhs, out, n);
     }
-    static SolverVT vt() { return SolverVT{NV, &factor, &forward, &backward, &top, &residual}; }
+    static void reduce(const ReduceArgs &a, int blocks, cudaStream_t st) {
+        newton_reduce_kernel<NV><<<blocks, 256, 0, st>>>(a);
+    }
+    static SolverVT vt() { return SolverVT{NV, &factor, &forward, &backward, &top, &residual, &reduce}; }
 };
 
 static bool solver_vt_for(int nv, SolverVT *out) {
@@ -156,7 +207,10 @@ struct rst_b200_solver {
     double *Ysave = nullptr;  // device-side checkpoint of Y (rst_b200_checkpoint)
     double *d_tmp = nullptr;  // [n*nv + nv] staging for reduced-order host drop-ins
     std::vector<void *> owned;
-    std::vector<LevelBuf> levels;      // local condensation levels
+    std::vector<LevelBuf> levels;      // local condensation levels (lanes-per-slab kernels)
+    bool use_tps = false;              // nv == 2: thread-per-slab kernels + single-CTA tail (tps.cuh)
+    std::vector<TpsLevel> tps_big;     // levels launched one kernel each
+    TpsTail tps_tail{};                // all remaining levels
     bool have_red = false;
     LevelBuf red{};                    // interface (reduced) level when world > 1
     double *iface_rows = nullptr;      // [2 nv^2]  (A | B) of the local condensed row
@@ -363,6 +417,48 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
             TRY(dev_alloc(s, &s->topB, (size_t)nv * nv));
             TRY(dev_alloc(s, &s->top_r, (size_t)nv));
         }
+        s->use_tps = (nv == 2) && (std::getenv("RST_B200_NO_TPS") == nullptr);
+        if (s->use_tps) {
+            // thread-per-slab levels (S = TPS_S): big levels one launch each, the rest inside the tail kernel
+            int64_t ln = n;
+            const double *lA = s->A, *lB = s->B, *lr = s->F;
+            double *lZ = s->dY;
+            s->tps_tail.nlevels = 0;
+            while (ln > 1) {
+                TpsLevel lv{};
+                lv.n = ln;
+                lv.nslabs = (ln + TPS_S - 1) / TPS_S;
+                lv.A = lA; lv.B = lB; lv.r = lr; lv.Z = lZ;
+                TRY(dev_alloc(s, &lv.fac, (size_t)(TPS_S - 1) * TpsCfg<2>::NE * lv.nslabs));
+                TRY(dev_alloc(s, &lv.bits, (size_t)(TPS_S - 1) * lv.nslabs));
+                TRY(dev_alloc(s, &lv.e, (size_t)(TPS_S - 1) * nv * lv.nslabs));
+                if (lv.nslabs > 1) {
+                    TRY(dev_alloc(s, &lv.A_next, (size_t)lv.nslabs * nv * nv));
+                    TRY(dev_alloc(s, &lv.B_next, (size_t)lv.nslabs * nv * nv));
+                    TRY(dev_alloc(s, &lv.r_next, (size_t)lv.nslabs * nv));
+                    double *zn = nullptr;
+                    TRY(dev_alloc(s, &zn, (size_t)(lv.nslabs + 1) * nv));
+                    lv.Z_next = zn;
+                } else {
+                    lv.A_next = s->iface_rows;
+                    lv.B_next = s->iface_rows + nv * nv;
+                    lv.r_next = s->iface_rhs;
+                    lv.Z_next = (world > 1) ? (s->Zred + (size_t)s->rank * nv) : s->Ztop;
+                }
+                if (ln > TPS_TAIL_ROWS) s->tps_big.push_back(lv);
+                else {
+                    if (s->tps_tail.nlevels >= TPS_MAX_TAIL_LEVELS) return fail(RST_B200_ERR_INVALID, "too many tail levels");
+                    s->tps_tail.lv[s->tps_tail.nlevels++] = lv;
+                }
+                lA = lv.A_next; lB = lv.B_next; lr = lv.r_next;
+                lZ = const_cast<double *>(lv.Z_next);
+                ln = lv.nslabs;
+            }
+            s->tps_tail.left_mask = s->left_mask;
+            s->tps_tail.right_mask = s->right_mask;
+            s->tps_tail.Ztop = s->Ztop;
+            s->tps_tail.do_top = (world == 1);
+        } else
         // local condensation levels: n -> ceil(n/S) -> ... -> 1
         {
             int64_t ln = n;
@@ -614,6 +710,18 @@ extern "C" int rst_b200_factor_local(rst_b200_solver *s) {
     if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
     if (!s->have_jac) return fail(RST_B200_ERR_NOT_FACTORIZED, "no Jacobian has been evaluated");
     CUDA_TRY(cudaMemsetAsync(s->d_flags, 0, sizeof(unsigned), s->stream));
+    if (s->use_tps) {
+        for (auto &lv : s->tps_big) {
+            const unsigned blocks = (unsigned)((lv.nslabs + 127) / 128);
+            if (lv.B == nullptr) tps_factor_kernel<2, TPS_S, true><<<blocks, 128, 0, s->stream>>>(lv, s->d_flags);
+            else tps_factor_kernel<2, TPS_S, false><<<blocks, 128, 0, s->stream>>>(lv, s->d_flags);
+            s->launches++;
+        }
+        tps_tail_factor_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, s->d_flags);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return RST_B200_OK;
+    }
     for (auto &lv : s->levels) {
         s->sv.factor(lv.k, lv.ident_b, s->d_flags, s->stream);
         s->launches++;
@@ -656,6 +764,18 @@ extern "C" int rst_b200_factor(rst_b200_solver *s) {
 extern "C" int rst_b200_solve_local_forward(rst_b200_solver *s) {
     if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
     if (!s->factored) return fail(RST_B200_ERR_NOT_FACTORIZED, "solve before factor");
+    if (s->use_tps) {
+        for (auto &lv : s->tps_big) {
+            tps_forward_kernel<2, TPS_S><<<(unsigned)((lv.nslabs + 127) / 128), 128, 0, s->stream>>>(lv);
+            s->launches++;
+        }
+        if (s->world > 1) {  // single GPU: the tail's forward sweep is fused with the closure + backward sweep below
+            tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, 1, s->d_flags);
+            s->launches++;
+        }
+        CUDA_TRY(cudaGetLastError());
+        return RST_B200_OK;
+    }
     for (auto &lv : s->levels) {
         s->sv.forward(lv.k, s->stream);
         s->launches++;
@@ -666,6 +786,17 @@ extern "C" int rst_b200_solve_local_forward(rst_b200_solver *s) {
 
 extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
     if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    if (s->use_tps && s->world == 1) {
+        tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, 7, s->d_flags);
+        s->launches++;
+        for (int i = (int)s->tps_big.size() - 1; i >= 0; --i) {
+            const TpsLevel &lv = s->tps_big[i];
+            tps_backward_kernel<2, TPS_S><<<(unsigned)((lv.nslabs + 127) / 128), 128, 0, s->stream>>>(lv);
+            s->launches++;
+        }
+        CUDA_TRY(cudaGetLastError());
+        return RST_B200_OK;
+    }
     const double *C, *D, *g;
     if (s->have_red) {
         CUDA_TRY(cudaMemcpyAsync(s->red_r, s->gath_rhs, (size_t)s->world * s->nv * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
@@ -680,6 +811,17 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
     if (s->have_red) {
         s->sv.backward(s->red.k, s->stream);
         s->launches++;
+    }
+    if (s->use_tps) {
+        tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, 4, s->d_flags);
+        s->launches++;
+        for (int i = (int)s->tps_big.size() - 1; i >= 0; --i) {
+            const TpsLevel &lv = s->tps_big[i];
+            tps_backward_kernel<2, TPS_S><<<(unsigned)((lv.nslabs + 127) / 128), 128, 0, s->stream>>>(lv);
+            s->launches++;
+        }
+        CUDA_TRY(cudaGetLastError());
+        return RST_B200_OK;
     }
     for (int i = (int)s->levels.size() - 1; i >= 0; --i) {
         s->sv.backward(s->levels[i].k, s->stream);
@@ -722,7 +864,7 @@ extern "C" int rst_b200_reduce_local(rst_b200_solver *s, int which_state) {
     a.has_left = (s->rank == 0); a.has_right = (s->rank == s->world - 1);
     a.partials = s->d_partials;
     a.n_rows = s->n;
-    newton_reduce_kernel<<<s->red_blocks, 256, 0, s->stream>>>(a);
+    s->sv.reduce(a, s->red_blocks, s->stream);
     newton_reduce_final_kernel<<<1, 256, 0, s->stream>>>(s->d_partials, s->red_blocks, s->d_scal, s->d_flags);
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());

@@ -1,0 +1,407 @@
+// tps.cuh -- "thread per slab" kernels of the pivoted condensation solver for tiny blocks (nv = 2: configs C1/C2).
+//
+// Same algorithm as abd.cuh (pivoted elimination of the node shared by the running condensed row and the next block
+// row, slab by slab, recursively), but for nv = 2 a 4 x 6 panel fits in one thread's registers: no shuffles, no shared
+// memory, slab length S is a compile-time constant so the whole slab is unrolled and its loads are issued up front.
+// The round-1 launch list (profiles/r01_a_summary.md) showed the lanes-per-slab kernels spend as long in the upper
+// levels (latency chains of S dependent steps behind every launch) as in level 0, so here
+//   * levels with more than TPS_TAIL_ROWS rows run one launch each,
+//   * all remaining levels, the boundary closure and their back-substitution run inside ONE single-CTA "tail" kernel
+//     (levels separated by __syncthreads, data L2 resident).
+// Pivoting: at elimination step k the rows k..2nv-1 are scanned with conditional swaps (static register indices); the
+// swap decisions are recorded as a bit mask and replayed on the right-hand side by the forward sweep.
+//
+// Factor storage (thread-interleaved, every access coalesced):   fac[((i-1)*NE + e) * nslabs + slab]
+//   e: [ L (k, row>k) | per k: 1/pivot, U(k, c>k) | E (k,c) | F (k,c) ],  bits[(i-1)*nslabs + slab], e_rhs likewise.
+#pragma once
+#include "rst_common.cuh"
+
+namespace rst {
+
+constexpr int TPS_S = 8;            // rows per slab (compile-time: the slab loop is fully unrolled)
+constexpr int TPS_TAIL_ROWS = 4096;
+constexpr int TPS_MAX_TAIL_LEVELS = 8;
+
+struct TpsLevel {
+    int64_t n, nslabs;
+    const double *A, *B;      // [n][nv][nv]; B == nullptr -> identity
+    double *A_next, *B_next;  // [nslabs][nv][nv]
+    double *fac;
+    unsigned *bits;
+    const double *r;          // [n][nv]
+    double *e;                // [(S-1)][nv][nslabs]
+    double *r_next;           // [nslabs][nv]
+    double *Z;                // [n+1][nv]
+    const double *Z_next;     // [nslabs+1][nv]
+};
+
+struct TpsTail {
+    int nlevels;
+    TpsLevel lv[TPS_MAX_TAIL_LEVELS];
+    // boundary closure (world == 1): C = last A_next, D = last B_next, g = last r_next
+    unsigned long long left_mask, right_mask;
+    double *Ztop;             // [2][nv]
+    int do_top;
+};
+
+template <int NV>
+struct TpsCfg {
+    static constexpr int R2 = 2 * NV;
+    static constexpr int NL = NV * (3 * NV - 1) / 2;  // sum_k (2nv-1-k)
+    static constexpr int NU = NV * (NV + 1) / 2;
+    static constexpr int NE = NL + NU + 2 * NV * NV;
+};
+
+// FULL = the slab has all S rows: every load is unconditional, so the unrolled body issues the whole slab's loads up
+// front instead of one dependent load per step (only the last slab of a level can be ragged).
+template <int NV, int S, bool IDENT_B, bool FULL>
+__device__ __forceinline__ void tps_factor_slab_impl(const TpsLevel &L, int64_t slab, unsigned *flags) {
+    using Cfg = TpsCfg<NV>;
+    constexpr int R2 = Cfg::R2, W = 3 * NV;
+    const int64_t g0 = slab * S;
+    const int len = FULL ? S : (int)((L.n - g0) < (int64_t)S ? (L.n - g0) : (int64_t)S);
+    double R[R2][W];
+#pragma unroll
+    for (int i = 0; i < R2; ++i)
+#pragma unroll
+        for (int c = 0; c < W; ++c) R[i][c] = 0.0;
+    // carry rows <- first block row of the slab: P = A, M = B
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+            R[i][NV + c] = L.A[(g0 * NV + i) * NV + c];
+            R[i][c] = IDENT_B ? ((i == c) ? 1.0 : 0.0) : L.B[(g0 * NV + i) * NV + c];
+        }
+    // all block rows of the slab are loaded before the dependent elimination chain starts
+    double An[S - 1][NV][NV], Bn[IDENT_B ? 1 : S - 1][NV][NV];
+#pragma unroll
+    for (int st = 1; st < S; ++st) {
+        const bool ok = FULL || st < len;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                An[st - 1][i][c] = ok ? L.A[((g0 + st) * NV + i) * NV + c] : 0.0;
+                if (!IDENT_B) Bn[st - 1][i][c] = ok ? L.B[((g0 + st) * NV + i) * NV + c] : 0.0;
+            }
+    }
+#pragma unroll
+    for (int st = 1; st < S; ++st) {
+        if (FULL || st < len) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+#pragma unroll
+                for (int c = 0; c < NV; ++c) {
+                    R[NV + i][c] = An[st - 1][i][c];
+                    R[NV + i][NV + c] = 0.0;
+                    R[NV + i][2 * NV + c] = IDENT_B ? ((i == c) ? 1.0 : 0.0) : Bn[IDENT_B ? 0 : st - 1][i][c];
+                }
+            double *fac = L.fac + ((int64_t)(st - 1) * Cfg::NE) * L.nslabs + slab;
+            unsigned bits = 0;
+            int bit = 0, le = 0;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+#pragma unroll
+                for (int ii = k + 1; ii < R2; ++ii) {
+                    const bool sw = fabs(R[ii][k]) > fabs(R[k][k]);
+                    bits |= (sw ? 1u : 0u) << bit;
+                    ++bit;
+#pragma unroll
+                    for (int c = k; c < W; ++c) {
+                        const double a = R[k][c], b = R[ii][c];
+                        R[k][c] = sw ? b : a;
+                        R[ii][c] = sw ? a : b;
+                    }
+                }
+                const double piv = R[k][k];
+                if (!(fabs(piv) > 0.0)) atomicOr(flags, RST_FLAG_ZERO_PIVOT);
+                const double rc = 1.0 / piv;
+                R[k][k] = rc;  // the diagonal slot keeps the reciprocal pivot
+#pragma unroll
+                for (int ii = k + 1; ii < R2; ++ii) {
+                    const double l = R[ii][k] * rc;
+                    fac[(int64_t)le * L.nslabs] = l;
+                    ++le;
+#pragma unroll
+                    for (int c = k + 1; c < W; ++c) R[ii][c] = fma(-l, R[k][c], R[ii][c]);
+                }
+            }
+            L.bits[(int64_t)(st - 1) * L.nslabs + slab] = bits;
+            int ue = Cfg::NL;
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+#pragma unroll
+                for (int c = k; c < NV; ++c) { fac[(int64_t)ue * L.nslabs] = R[k][c]; ++ue; }
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+#pragma unroll
+                for (int c = 0; c < NV; ++c) { fac[(int64_t)ue * L.nslabs] = R[k][NV + c]; ++ue; }
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+#pragma unroll
+                for (int c = 0; c < NV; ++c) { fac[(int64_t)ue * L.nslabs] = R[k][2 * NV + c]; ++ue; }
+            // survivors become the carry rows: M <- Q', P <- P', Q <- 0
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+#pragma unroll
+                for (int c = 0; c < NV; ++c) {
+                    R[i][NV + c] = R[NV + i][NV + c];
+                    R[i][c] = R[NV + i][2 * NV + c];
+                    R[i][2 * NV + c] = 0.0;
+                }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+            L.A_next[(slab * NV + i) * NV + c] = R[i][NV + c];
+            L.B_next[(slab * NV + i) * NV + c] = R[i][c];
+        }
+}
+
+template <int NV, int S, bool IDENT_B>
+__device__ __forceinline__ void tps_factor_slab(const TpsLevel &L, int64_t slab, unsigned *flags) {
+    if ((slab + 1) * S <= L.n) tps_factor_slab_impl<NV, S, IDENT_B, true>(L, slab, flags);
+    else tps_factor_slab_impl<NV, S, IDENT_B, false>(L, slab, flags);
+}
+
+template <int NV, int S, bool FULL>
+__device__ __forceinline__ void tps_forward_slab_impl(const TpsLevel &L, int64_t slab) {
+    using Cfg = TpsCfg<NV>;
+    constexpr int R2 = Cfg::R2;
+    const int64_t g0 = slab * S;
+    const int len = FULL ? S : (int)((L.n - g0) < (int64_t)S ? (L.n - g0) : (int64_t)S);
+    double w[R2];
+    // every load of the slab is issued before the dependent elimination chain starts
+    double lf[S - 1][Cfg::NL], rr[S - 1][NV];
+    unsigned bt[S - 1];
+#pragma unroll
+    for (int st = 1; st < S; ++st) {
+        const bool ok = FULL || st < len;
+        const double *fac = L.fac + ((int64_t)(st - 1) * Cfg::NE) * L.nslabs + slab;
+#pragma unroll
+        for (int e = 0; e < Cfg::NL; ++e) lf[st - 1][e] = ok ? __ldcs(fac + (int64_t)e * L.nslabs) : 0.0;
+        bt[st - 1] = ok ? __ldcs(L.bits + (int64_t)(st - 1) * L.nslabs + slab) : 0u;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) rr[st - 1][i] = ok ? L.r[(g0 + st) * NV + i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { w[i] = L.r[g0 * NV + i]; w[NV + i] = 0.0; }
+#pragma unroll
+    for (int st = 1; st < S; ++st) {
+        if (FULL || st < len) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) w[NV + i] = rr[st - 1][i];
+            const double *fac = lf[st - 1];
+            const unsigned bits = bt[st - 1];
+            int bit = 0, le = 0;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+#pragma unroll
+                for (int ii = k + 1; ii < R2; ++ii) {
+                    const bool sw = (bits >> bit) & 1u;
+                    ++bit;
+                    const double a = w[k], b = w[ii];
+                    w[k] = sw ? b : a;
+                    w[ii] = sw ? a : b;
+                }
+#pragma unroll
+                for (int ii = k + 1; ii < R2; ++ii) {
+                    w[ii] = fma(-fac[le], w[k], w[ii]);
+                    ++le;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                L.e[((int64_t)(st - 1) * NV + k) * L.nslabs + slab] = w[k];
+                w[k] = w[NV + k];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) L.r_next[slab * NV + i] = w[i];
+}
+
+template <int NV, int S>
+__device__ __forceinline__ void tps_forward_slab(const TpsLevel &L, int64_t slab) {
+    if ((slab + 1) * S <= L.n) tps_forward_slab_impl<NV, S, true>(L, slab);
+    else tps_forward_slab_impl<NV, S, false>(L, slab);
+}
+
+template <int NV, int S, bool FULL>
+__device__ __forceinline__ void tps_backward_slab_impl(const TpsLevel &L, int64_t slab) {
+    using Cfg = TpsCfg<NV>;
+    const int64_t g0 = slab * S;
+    const int len = FULL ? S : (int)((L.n - g0) < (int64_t)S ? (L.n - g0) : (int64_t)S);
+    double Ys[NV], Yn[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+        Ys[c] = L.Z_next[slab * NV + c];
+        Yn[c] = L.Z_next[(slab + 1) * NV + c];
+        L.Z[g0 * NV + c] = Ys[c];
+    }
+    if (slab == L.nslabs - 1) {
+#pragma unroll
+        for (int c = 0; c < NV; ++c) L.Z[L.n * NV + c] = Yn[c];
+    }
+    // all loads of the slab first; the part of the right-hand side that only needs Y_s is folded in as data arrives,
+    // so the dependent chain per step is just F * Y_next and the nv x nv triangular solve
+    double Us[S - 1][NV][NV], Fs[S - 1][NV][NV], ts[S - 1][NV];
+#pragma unroll
+    for (int st = S - 1; st >= 1; --st) {
+        const bool ok = FULL || st < len;
+        const double *fac = L.fac + ((int64_t)(st - 1) * Cfg::NE) * L.nslabs + slab;
+        int ue = Cfg::NL;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int c = k; c < NV; ++c) { Us[st - 1][k][c] = ok ? __ldcs(fac + (int64_t)ue * L.nslabs) : 1.0; ++ue; }
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+            ts[st - 1][k] = ok ? __ldcs(L.e + ((int64_t)(st - 1) * NV + k) * L.nslabs + slab) : 0.0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                const double ev = ok ? __ldcs(fac + (int64_t)ue * L.nslabs) : 0.0;
+                ts[st - 1][k] = fma(-ev, Ys[c], ts[st - 1][k]);
+                ++ue;
+            }
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int c = 0; c < NV; ++c) { Fs[st - 1][k][c] = ok ? __ldcs(fac + (int64_t)ue * L.nslabs) : 0.0; ++ue; }
+    }
+#pragma unroll
+    for (int st = S - 1; st >= 1; --st) {
+        if (FULL || st < len) {
+            double t[NV];
+            const double (*U)[NV] = Us[st - 1];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                t[k] = ts[st - 1][k];
+#pragma unroll
+                for (int c = 0; c < NV; ++c) t[k] = fma(-Fs[st - 1][k][c], Yn[c], t[k]);
+            }
+#pragma unroll
+            for (int k = NV - 1; k >= 0; --k) {
+                double s = t[k];
+#pragma unroll
+                for (int c = k + 1; c < NV; ++c) s = fma(-U[k][c], Yn[c], s);
+                Yn[k] = s * U[k][k];  // U[k][k] holds 1/pivot
+            }
+            const int64_t g = g0 + st;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) L.Z[g * NV + c] = Yn[c];
+        }
+    }
+}
+
+template <int NV, int S>
+__device__ __forceinline__ void tps_backward_slab(const TpsLevel &L, int64_t slab) {
+    if ((slab + 1) * S <= L.n) tps_backward_slab_impl<NV, S, true>(L, slab);
+    else tps_backward_slab_impl<NV, S, false>(L, slab);
+}
+
+// ---- one launch per level (big levels) ------------------------------------------------------------
+template <int NV, int S, bool IDENT_B>
+__global__ void __launch_bounds__(128) tps_factor_kernel(TpsLevel L, unsigned *flags) {
+    const int64_t slab = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slab < L.nslabs) tps_factor_slab<NV, S, IDENT_B>(L, slab, flags);
+}
+template <int NV, int S>
+__global__ void __launch_bounds__(128) tps_forward_kernel(TpsLevel L) {
+    const int64_t slab = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slab < L.nslabs) tps_forward_slab<NV, S>(L, slab);
+}
+template <int NV, int S>
+__global__ void __launch_bounds__(128) tps_backward_kernel(TpsLevel L) {
+    const int64_t slab = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slab < L.nslabs) tps_backward_slab<NV, S>(L, slab);
+}
+
+// ---- the tail: every remaining level inside one CTA -----------------------------------------------
+template <int NV, int S>
+__global__ void __launch_bounds__(256) tps_tail_factor_kernel(TpsTail T, unsigned *flags) {
+    for (int l = 0; l < T.nlevels; ++l) {
+        const TpsLevel &L = T.lv[l];
+        for (int64_t slab = threadIdx.x; slab < L.nslabs; slab += blockDim.x) {
+            // one generic (predicated-load) variant per case keeps the single CTA's straight-line code -- and with it
+            // the cold instruction-fetch cost that dominates a one-CTA kernel -- small
+            if (L.B == nullptr) tps_factor_slab_impl<NV, S, true, false>(L, slab, flags);  // small meshes: level 0 in the tail
+            else tps_factor_slab_impl<NV, S, false, false>(L, slab, flags);
+        }
+        __syncthreads();
+    }
+}
+
+// boundary closure, serial in one thread (nv x nv, nv tiny): C Z0 + D Z1 = g with pinned components removed
+template <int NV>
+__device__ void tps_top_solve(const double *C, const double *D, const double *g, double *Z,
+                              unsigned long long left_mask, unsigned long long right_mask, unsigned *flags) {
+    double K[NV][NV + 1];
+    int colmap[NV];
+    int nc = 0;
+    for (int c = 0; c < NV; ++c)
+        if (!((left_mask >> c) & 1ull)) { if (nc < NV) colmap[nc] = c; ++nc; }
+    for (int c = 0; c < NV; ++c)
+        if (!((right_mask >> c) & 1ull)) { if (nc < NV) colmap[nc] = NV + c; ++nc; }
+    if (nc != NV) { atomicOr(flags, RST_FLAG_ZERO_PIVOT); return; }
+    for (int row = 0; row < NV; ++row) {
+        for (int cc = 0; cc < NV; ++cc) {
+            const int cm = colmap[cc];
+            K[row][cc] = cm < NV ? C[row * NV + cm] : D[row * NV + (cm - NV)];
+        }
+        K[row][NV] = g[row];
+    }
+    for (int k = 0; k < NV; ++k) {
+        int p = k;
+        double best = fabs(K[k][k]);
+        for (int row = k + 1; row < NV; ++row)
+            if (fabs(K[row][k]) > best) { best = fabs(K[row][k]); p = row; }
+        if (!(best > 0.0)) atomicOr(flags, RST_FLAG_ZERO_PIVOT);
+        if (p != k)
+            for (int c = 0; c <= NV; ++c) { const double tmp = K[k][c]; K[k][c] = K[p][c]; K[p][c] = tmp; }
+        for (int row = k + 1; row < NV; ++row) {
+            const double l = K[row][k] / K[k][k];
+            for (int c = k + 1; c <= NV; ++c) K[row][c] = fma(-l, K[k][c], K[row][c]);
+        }
+    }
+    for (int row = NV - 1; row >= 0; --row) {
+        double s = K[row][NV];
+        for (int c = row + 1; c < NV; ++c) s = fma(-K[row][c], K[c][NV], s);
+        K[row][NV] = s / K[row][row];
+    }
+    for (int c = 0; c < 2 * NV; ++c) Z[c] = 0.0;
+    for (int cc = 0; cc < NV; ++cc) Z[colmap[cc]] = K[cc][NV];
+}
+
+// phases: bit 0 forward sweeps, bit 1 boundary closure, bit 2 backward sweeps
+template <int NV, int S>
+__global__ void __launch_bounds__(256) tps_tail_solve_kernel(TpsTail T, int phases, unsigned *flags) {
+    if (phases & 1) {
+        for (int l = 0; l < T.nlevels; ++l) {
+            const TpsLevel &L = T.lv[l];
+            for (int64_t slab = threadIdx.x; slab < L.nslabs; slab += blockDim.x) tps_forward_slab_impl<NV, S, false>(L, slab);
+            __syncthreads();
+        }
+    }
+    if (phases & 2) {
+        if (threadIdx.x == 0) {
+            const TpsLevel &L = T.lv[T.nlevels - 1];
+            tps_top_solve<NV>(L.A_next, L.B_next, L.r_next, T.Ztop, T.left_mask, T.right_mask, flags);
+        }
+        __syncthreads();
+    }
+    if (phases & 4) {
+        for (int l = T.nlevels - 1; l >= 0; --l) {
+            const TpsLevel &L = T.lv[l];
+            for (int64_t slab = threadIdx.x; slab < L.nslabs; slab += blockDim.x) tps_backward_slab_impl<NV, S, false>(L, slab);
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace rst

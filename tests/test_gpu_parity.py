@@ -254,7 +254,7 @@ def test_config_c3_million_points_newton_converges_and_residual_vanishes():
     # mesh-independent convergence: within one iteration of the coarse-mesh oracle count (5 at N = 2000)
     assert abs(st["number of iterations"] - ref.iterations) <= 1
     r = g.fun_call(sol)
-    assert np.linalg.norm(r) < 1e-6
+    assert np.max(np.abs(r)) < 1e-8   # convergence is on the step norm; per-row residuals are at rounding level
     # coarse-vs-fine agreement of the profiles at shared nodes (first-order scheme: O(h) apart)
     fine = g.get_result()[:: n // 2000]
     coarse = o.full_solution(ref.y)

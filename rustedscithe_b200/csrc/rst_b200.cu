@@ -606,63 +606,67 @@ static inline int64_t reduced_index(const rst_b200_solver *s, int64_t g, int v) 
     return g * (int64_t)nv + v - s->layout.nl;
 }
 
-extern "C" int rst_b200_set_state(rst_b200_solver *s, const double *y, size_t len) {
-    if (!s || !y) return fail(RST_B200_ERR_INVALID, "null argument");
-    if ((int64_t)len != s->N * (int64_t)s->nv) return fail(RST_B200_ERR_INVALID, "reduced state length mismatch");
+// The reduced unknown vector is the full node-major state with the pinned slots of node 0 and node N deleted
+// (numeric_discretization.rs:80-106), so every interior node is one contiguous run in both orderings: the state moves
+// with ONE large copy straight between the caller's buffer and HBM plus two nv-sized boundary copies.
+static int move_state(rst_b200_solver *s, double *y, bool to_device) {
     const int nv = s->nv;
-    if (s->world == 1) {
-        // one H2D copy of the reduced vector, expansion on the device
-        CUDA_TRY(cudaMemcpyAsync(s->d_tmp, y, len * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-        scatter_reduced_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->layout, s->d_tmp, s->Y);
-        s->launches++;
-        double pins[128];
-        for (int v = 0; v < nv; ++v) { pins[v] = s->left_val[v]; pins[nv + v] = s->right_val[v]; }
-        for (int v = 0; v < nv; ++v) {
-            if ((s->left_mask >> v) & 1ull)
-                CUDA_TRY(cudaMemcpyAsync(s->Y + v, &pins[v], sizeof(double), cudaMemcpyHostToDevice, s->stream));
-            if ((s->right_mask >> v) & 1ull)
-                CUDA_TRY(cudaMemcpyAsync(s->Y + s->N * nv + v, &pins[nv + v], sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    const int nl = s->layout.nl;
+    const int64_t g_lo = s->j_begin, g_hi = s->j_begin + s->n;          // local nodes [g_lo, g_hi]
+    const int64_t own_hi = (s->rank == s->world - 1) ? g_hi : g_hi - 1;  // nodes this rank reports back
+    const int64_t i_lo = g_lo < 1 ? 1 : g_lo;
+    const int64_t i_hi_set = g_hi > s->N - 1 ? s->N - 1 : g_hi;          // interior nodes (set: incl. halo)
+    const int64_t i_hi_get = own_hi > s->N - 1 ? s->N - 1 : own_hi;
+    const int64_t i_hi = to_device ? i_hi_set : i_hi_get;
+    if (i_hi >= i_lo) {
+        double *dev = s->Y + (i_lo - g_lo) * nv;
+        double *host = y + (i_lo * nv - nl);
+        const size_t bytes = (size_t)(i_hi - i_lo + 1) * nv * sizeof(double);
+        if (to_device) CUDA_TRY(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s->stream));
+        else CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+    }
+    double edge[128];
+    const bool has0 = (g_lo == 0), hasN = to_device ? (g_hi == s->N) : (own_hi == s->N);
+    if (to_device) {
+        if (has0) {
+            for (int v = 0, k = 0; v < nv; ++v) edge[v] = ((s->left_mask >> v) & 1ull) ? s->left_val[v] : y[k++];
+            CUDA_TRY(cudaMemcpyAsync(s->Y, edge, nv * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        }
+        if (hasN) {
+            const double *src = y + (s->N * (int64_t)nv - nl);
+            for (int v = 0, k = 0; v < nv; ++v) edge[64 + v] = ((s->right_mask >> v) & 1ull) ? s->right_val[v] : src[k++];
+            CUDA_TRY(cudaMemcpyAsync(s->Y + (s->N - g_lo) * nv, edge + 64, nv * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         }
         CUDA_TRY(cudaStreamSynchronize(s->stream));
     } else {
-        std::vector<double> full((size_t)(s->n + 1) * nv);
-        for (int64_t i = 0; i <= s->n; ++i) {
-            const int64_t g = s->j_begin + i;
-            for (int v = 0; v < nv; ++v) {
-                const int64_t k = reduced_index(s, g, v);
-                full[i * nv + v] = k >= 0 ? y[k] : (g == 0 ? s->left_val[v] : s->right_val[v]);
-            }
-        }
-        CUDA_TRY(cudaMemcpyAsync(s->Y, full.data(), full.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        if (has0) CUDA_TRY(cudaMemcpyAsync(edge, s->Y, nv * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        if (hasN) CUDA_TRY(cudaMemcpyAsync(edge + 64, s->Y + (s->N - g_lo) * nv, nv * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (has0)
+            for (int v = 0, k = 0; v < nv; ++v)
+                if (!((s->left_mask >> v) & 1ull)) y[k++] = edge[v];
+        if (hasN) {
+            double *dst = y + (s->N * (int64_t)nv - nl);
+            for (int v = 0, k = 0; v < nv; ++v)
+                if (!((s->right_mask >> v) & 1ull)) dst[k++] = edge[64 + v];
+        }
     }
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_set_state(rst_b200_solver *s, const double *y, size_t len) {
+    if (!s || !y) return fail(RST_B200_ERR_INVALID, "null argument");
+    if ((int64_t)len != s->N * (int64_t)s->nv) return fail(RST_B200_ERR_INVALID, "reduced state length mismatch");
+    TRY(move_state(s, const_cast<double *>(y), true));
     s->have_jac = s->factored = false;
     return RST_B200_OK;
 }
 
+// world > 1: only the unknowns of the nodes this rank owns are written
 extern "C" int rst_b200_get_state(rst_b200_solver *s, double *y, size_t len) {
     if (!s || !y) return fail(RST_B200_ERR_INVALID, "null argument");
     if ((int64_t)len != s->N * (int64_t)s->nv) return fail(RST_B200_ERR_INVALID, "reduced state length mismatch");
-    const int nv = s->nv;
-    if (s->world == 1) {
-        gather_reduced_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->layout, s->Y, s->d_tmp);
-        s->launches++;
-        CUDA_TRY(cudaMemcpyAsync(y, s->d_tmp, len * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(cudaStreamSynchronize(s->stream));
-    } else {
-        std::vector<double> full((size_t)(s->n + 1) * nv);
-        CUDA_TRY(cudaMemcpyAsync(full.data(), s->Y, full.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(cudaStreamSynchronize(s->stream));
-        const int64_t last = (s->rank == s->world - 1) ? s->n : s->n - 1;  // owned nodes
-        for (int64_t i = 0; i <= last; ++i) {
-            const int64_t g = s->j_begin + i;
-            for (int v = 0; v < nv; ++v) {
-                const int64_t k = reduced_index(s, g, v);
-                if (k >= 0) y[k] = full[i * nv + v];
-            }
-        }
-    }
-    return RST_B200_OK;
+    return move_state(s, y, false);
 }
 
 extern "C" int rst_b200_get_full_solution(rst_b200_solver *s, double *full, size_t len) {

@@ -139,6 +139,22 @@ int rst_b200_newton_solve(rst_b200_solver *s, const rst_b200_newton_opts *opts, 
 int rst_b200_newton_iterate(rst_b200_solver *s, const rst_b200_newton_opts *opts, int recalc_jacobian,
                             rst_b200_newton_stats *stats);
 
+/* frozen-Jacobian Newton (NR_Damp_solver_frozen.rs:1035-1148): y_new = y - J^-1 F(y), converged when
+ * ||y_new - y||_2 < tolerance, Jacobian recalculated per the reference's strategies (BVP_utils.rs:362-480) */
+#define RST_B200_FROZEN_NAIVE 0         /* "Naive": every iteration */
+#define RST_B200_FROZEN_FROZEN_NAIVE 1  /* "Frozen_naive": first iteration only */
+#define RST_B200_FROZEN_EVERY_M 2       /* "every_m" {m} */
+#define RST_B200_FROZEN_AT_HIGH_NORM 3  /* "at_high_morm" {norm} */
+#define RST_B200_FROZEN_AT_LOW_SPEED 4  /* "at_low_speed" {rate} */
+#define RST_B200_FROZEN_COMPLEX 5       /* "complex" {m, norm, rate} */
+typedef struct {
+    int strategy;
+    double strategy_params[3];
+    double tolerance;
+    int max_iterations;
+} rst_b200_frozen_opts;
+int rst_b200_newton_frozen(rst_b200_solver *s, const rst_b200_frozen_opts *opts, rst_b200_newton_stats *stats);
+
 /* ---- host-pointer drop-ins ---------------------------------------------------------------------- */
 /* DirectLinearSolver::solve_in_place (solver_traits.rs:3-14): rhs[N*nv] in the reference's row order,
  * overwritten with the solution in the reference's reduced column order. Needs rst_b200_factor. */
@@ -176,6 +192,19 @@ int rst_b200_solve_local_forward(rst_b200_solver *s);
 int rst_b200_solve_reduced_backward(rst_b200_solver *s);
 int rst_b200_reduce_local(rst_b200_solver *s, int which_state);
 int rst_b200_reduce_finish(rst_b200_solver *s, rst_b200_scalars *out);
+
+/* ---- BlockTridiagonal drop-in (src/somelinalg/banded/block_tridiagonal.rs:3-19,
+ *      block_tridiagonal_lu_consistent.rs:28, :98-247): BlockTridiagonalLuConsistent::{new, factor_from,
+ *      solve_in_place, solve_multiple_in_place}.  Blocks are row-major bs x bs; lower[k] = block (k+1, k),
+ *      upper[k] = block (k, k+1).  Unlike the reference, pivoting runs across neighbouring block rows, so singular
+ *      diagonal blocks are accepted when the matrix itself is non-singular.  Block sizes 1, 2, 3, 4, 6, 8. ---- */
+typedef struct rst_b200_btd rst_b200_btd;
+int rst_b200_btd_create(int64_t n_blocks, int block_size, int device, void *stream, rst_b200_btd **out);
+void rst_b200_btd_destroy(rst_b200_btd *s);
+int64_t rst_b200_btd_n(const rst_b200_btd *s);
+int rst_b200_btd_factor_from(rst_b200_btd *s, const double *lower, const double *diag, const double *upper);
+int rst_b200_btd_solve_in_place(rst_b200_btd *s, double *rhs, size_t len);
+int rst_b200_btd_solve_multiple_in_place(rst_b200_btd *s, double *rhs, size_t nrhs, size_t ldb);
 
 /* synchronous cudaMemcpy on raw pointers (kind: 1 H2D, 2 D2H, 3 D2D) -- lets a host language without CUDA
  * bindings move data to / from rst_b200_device_ptr buffers */

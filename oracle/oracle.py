@@ -160,6 +160,9 @@ class NewtonResult:
     y: np.ndarray
 
 
+FROZEN_STRATEGIES = {"Naive": 0, "Frozen_naive": 1, "every_m": 2, "at_high_morm": 3, "at_low_speed": 4, "complex": 5}
+
+
 class OracleBVP:
     """Discretised BVP on the CPU oracle: layout, residual, Jacobian stream, band layouts, Newton."""
 
@@ -253,6 +256,17 @@ class OracleBVP:
         o = _NewtonOpts(max_iterations, max_jac, max_damp_iter, damp_factor, abs_tol, 1 if refactor_per_solve else 0)
         st = _NewtonStats()
         self.L.orc_newton_damped(C.byref(self.bvp), C.byref(o), _p(lo), _p(hi), _p(rtol), _p(y), C.byref(st))
+        return NewtonResult(st.status, st.iterations, st.linear_solves, st.jac_recalcs, st.factorizations,
+                            st.last_s1, st.last_conv, st.t_fun, st.t_jac, st.t_lin, y)
+
+    def newton_frozen(self, y0, strategy="Frozen_naive", strategy_params=(), tolerance=1e-6, max_iterations=25,
+                      refactor_per_solve=True) -> NewtonResult:
+        sid = FROZEN_STRATEGIES[strategy]
+        y = _f64(y0).copy()
+        sp = _f64(list(strategy_params) + [0.0] * (3 - len(strategy_params)))
+        st = _NewtonStats()
+        self.L.orc_newton_frozen(C.byref(self.bvp), sid, _p(sp), C.c_double(tolerance), max_iterations,
+                                 1 if refactor_per_solve else 0, _p(y), C.byref(st))
         return NewtonResult(st.status, st.iterations, st.linear_solves, st.jac_recalcs, st.factorizations,
                             st.last_s1, st.last_conv, st.t_fun, st.t_jac, st.t_lin, y)
 

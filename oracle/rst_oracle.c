@@ -615,3 +615,73 @@ int orc_newton_damped(const orc_bvp *b, const orc_newton_opts *o, const double *
     free(c.banded); free(c.ab); free(c.ipiv); free(step0); free(step1); free(y1);
     return status;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Frozen-Jacobian Newton.  src/numerical/BVP_Damp/NR_Damp_solver_frozen.rs:1035-1096 (iteration: F(y), Jacobian
+ * when jac_recalc else m += 1, delta = J^-1 F, y_new = y - delta), :1105-1148 (try_main_loop: error = ||y_new - y||,
+ * converged when error < tolerance), recalculation strategies BVP_utils.rs:362-480 (frozen_jac_recalc).
+ * strategy: 0 Naive, 1 Frozen_naive, 2 every_m {m}, 3 at_high_morm {norm}, 4 at_low_speed {rate},
+ * 5 complex {m, norm, rate}.  Linear solves refactor every time (BVP_traits.rs:875-899) when refactor_per_solve.
+ * ---------------------------------------------------------------------------------------------- */
+static int frozen_recalc(int strategy, const double *sp, int have_jac, int m, double error, double error_old) {
+    switch (strategy) {
+        case 0: return 1;
+        case 1: return !have_jac;
+        case 2: return (!have_jac || m > (int)sp[0]);
+        case 3: return error > sp[0];
+        case 4: return sp[0] * error_old < error;
+        case 5: return (error > sp[1]) || (m > (int)sp[0]) || (sp[2] * error_old < error);
+        default: return 1;
+    }
+}
+
+int orc_newton_frozen(const orc_bvp *b, int strategy, const double *sp, double tolerance, int max_iterations,
+                      int refactor_per_solve, double *y, orc_newton_stats *st) {
+    nctx c;
+    orc_newton_opts o;
+    memset(&c, 0, sizeof(c));
+    memset(&o, 0, sizeof(o));
+    memset(st, 0, sizeof(*st));
+    o.refactor_per_solve = refactor_per_solve;
+    c.b = b; c.st = st; c.o = &o;
+    c.n = (int64_t)b->nv * b->n_steps;
+    c.nnz = orc_jacobian_structure(b, NULL, NULL, NULL, NULL, &c.kl, &c.ku);
+    c.rows = (int64_t *)malloc(sizeof(int64_t) * (size_t)c.nnz);
+    c.cols = (int64_t *)malloc(sizeof(int64_t) * (size_t)c.nnz);
+    c.doff = (int64_t *)malloc(sizeof(int64_t) * (size_t)c.nnz);
+    c.dpos = (int64_t *)malloc(sizeof(int64_t) * (size_t)c.nnz);
+    orc_jacobian_structure(b, c.rows, c.cols, c.doff, c.dpos, &c.kl, &c.ku);
+    c.values = (double *)malloc(sizeof(double) * (size_t)c.nnz);
+    c.diags = (double *)malloc(sizeof(double) * (size_t)orc_assembly_size(c.n, c.kl, c.ku, NULL));
+    c.banded = (double *)malloc(sizeof(double) * (size_t)(c.kl + c.ku + 1) * (size_t)c.n);
+    c.ab = (double *)malloc(sizeof(double) * (size_t)(2 * c.kl + c.ku + 1) * (size_t)c.n);
+    c.ipiv = (int64_t *)malloc(sizeof(int64_t) * (size_t)c.n);
+    double *delta = (double *)malloc(sizeof(double) * (size_t)c.n);
+    int jac_recalc = 1, have_jac = 0, m = 0, status = 0, it = 0;
+    double error_old = 0.0;
+    while (it < max_iterations) {
+        st->iterations++;
+        if (jac_recalc) {
+            orc_jacobian_values(b, y, c.rows, c.cols, c.nnz, c.values);
+            orc_assemble_diagonals(c.n, c.kl, c.ku, c.nnz, c.doff, c.dpos, c.values, c.diags);
+            have_jac = 1; c.have_factor = 0; m = 0;
+            st->jac_recalcs++;
+        } else {
+            m += 1;
+        }
+        const int rc = newton_step(&c, y, delta); /* F(y) then delta = J^-1 F */
+        if (rc) { status = rc; break; }
+        st->linear_solves++;
+        for (int64_t i = 0; i < c.n; ++i) y[i] = y[i] - delta[i];
+        const double error = orc_norm2(c.n, delta);
+        jac_recalc = frozen_recalc(strategy, sp, have_jac, m, error, error_old);
+        error_old = error;
+        st->last_s1 = error;
+        if (error < tolerance) { status = 1; break; }
+        it += 1;
+    }
+    st->status = status;
+    free(c.rows); free(c.cols); free(c.doff); free(c.dpos); free(c.values); free(c.diags);
+    free(c.banded); free(c.ab); free(c.ipiv); free(delta);
+    return status;
+}

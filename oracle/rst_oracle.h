@@ -120,6 +120,10 @@ typedef struct {
 /* y[n] in: initial reduced guess (used verbatim, NR_Damp_solver_damped.rs:2034-2040); out: result */
 int orc_newton_damped(const orc_bvp *b, const orc_newton_opts *o, const double *lo, const double *hi,
                       const double *rtol, double *y, orc_newton_stats *st);
+/* frozen-Jacobian Newton (NR_Damp_solver_frozen.rs:1035-1148, BVP_utils.rs:362-480); strategy: 0 Naive,
+ * 1 Frozen_naive, 2 every_m{m}, 3 at_high_morm{norm}, 4 at_low_speed{rate}, 5 complex{m,norm,rate} */
+int orc_newton_frozen(const orc_bvp *b, int strategy, const double *strategy_params, double tolerance,
+                      int max_iterations, int refactor_per_solve, double *y, orc_newton_stats *st);
 /* re-insert BC values (BVP_utils.rs:534-558): full[(n_steps+1)*nv] */
 void orc_construct_full_solution(const orc_bvp *b, const double *y_reduced, double *full);
 

@@ -370,3 +370,66 @@ __global__ void __launch_bounds__(32) abd_top_solve_kernel(const double *C, cons
 }
 
 }  // namespace rst
+
+namespace rst {
+
+// ------------------------------------------------------------------------------------------------
+// Closure with GENERAL separated boundary rows (used by the block-tridiagonal drop-in, btd.cuh):
+//   Ba Z0 = ba (na rows),  C Z0 + D Z1 = g (nv rows),  Bb Z1 = bb (nb rows),  na + nb = nv
+// -> one dense 2nv x 2nv system, partial pivoting in shared memory, one warp.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(32) abd_top_general_kernel(const double *C, const double *D, const double *g,
+                                                             const double *Ba, const double *ba, int na,
+                                                             const double *Bb, const double *bb, int nb, double *Z,
+                                                             unsigned *flags) {
+    constexpr int N2 = 2 * NV;
+    __shared__ double K[N2][N2 + 1];
+    const int lane = threadIdx.x;
+    for (int idx = lane; idx < N2 * (N2 + 1); idx += 32) (&K[0][0])[idx] = 0.0;
+    __syncwarp();
+    for (int idx = lane; idx < na * NV; idx += 32) K[idx / NV][idx % NV] = Ba[idx];
+    for (int idx = lane; idx < na; idx += 32) K[idx][N2] = ba[idx];
+    for (int idx = lane; idx < NV * NV; idx += 32) {
+        K[na + idx / NV][idx % NV] = C[idx];
+        K[na + idx / NV][NV + idx % NV] = D[idx];
+    }
+    for (int idx = lane; idx < NV; idx += 32) K[na + idx][N2] = g[idx];
+    for (int idx = lane; idx < nb * NV; idx += 32) K[na + NV + idx / NV][NV + idx % NV] = Bb[idx];
+    for (int idx = lane; idx < nb; idx += 32) K[na + NV + idx][N2] = bb[idx];
+    __syncwarp();
+    for (int k = 0; k < N2; ++k) {
+        double best = -1.0;
+        int bi = k;
+        for (int row = k + lane; row < N2; row += 32) {
+            const double v = fabs(K[row][k]);
+            if (v > best) { best = v; bi = row; }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const double ob = __shfl_xor_sync(RST_FULL_MASK, best, off);
+            const int oi = __shfl_xor_sync(RST_FULL_MASK, bi, off);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (!(best > 0.0) && lane == 0) atomicOr(flags, RST_FLAG_ZERO_PIVOT);
+        if (bi != k)
+            for (int c = lane; c <= N2; c += 32) { const double tmp = K[k][c]; K[k][c] = K[bi][c]; K[bi][c] = tmp; }
+        __syncwarp();
+        const double pivval = K[k][k];
+        for (int row = k + 1 + lane; row < N2; row += 32) {
+            const double l = K[row][k] / pivval;
+            for (int c = k + 1; c <= N2; ++c) K[row][c] = fma(-l, K[k][c], K[row][c]);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        for (int row = N2 - 1; row >= 0; --row) {
+            double s = K[row][N2];
+            for (int c = row + 1; c < N2; ++c) s = fma(-K[row][c], K[c][N2], s);
+            K[row][N2] = s / K[row][row];
+        }
+        for (int c = 0; c < N2; ++c) Z[c] = K[c][N2];
+    }
+}
+
+}  // namespace rst

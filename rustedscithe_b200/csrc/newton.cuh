@@ -43,46 +43,52 @@ __device__ __forceinline__ double warp_min(double v) {
 template <int NV>
 __global__ void __launch_bounds__(256) newton_reduce_kernel(ReduceArgs a) {
     double ss = 0.0, tol = 0.0, fb = 1.0, nanf = 0.0;
-    double lo[NV], hi[NV], rt[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) { lo[v] = a.lo[v]; hi[v] = a.hi[v]; rt[v] = a.rtol[v]; }
-    // one thread per node: nv contiguous doubles of y and of the step (vectorised), no index division
-    for (int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; node < a.n_nodes;
-         node += (int64_t)gridDim.x * blockDim.x) {
-        unsigned long long pinmask = 0ull;
-        if (a.has_left && node == 0) pinmask |= a.left_mask;
-        if (a.has_right && node == a.n_nodes - 1) pinmask |= a.right_mask;
-        double yv[NV], sv[NV];
-        if constexpr (NV % 2 == 0) {
-            const double2 *y2 = reinterpret_cast<const double2 *>(a.Y + node * NV);
-            const double2 *s2 = reinterpret_cast<const double2 *>(a.dY + node * NV);
-#pragma unroll
-            for (int v = 0; v < NV; v += 2) {
-                const double2 p = y2[v >> 1], q = s2[v >> 1];
-                yv[v] = p.x; yv[v + 1] = p.y; sv[v] = q.x; sv[v + 1] = q.y;
-            }
-        } else {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) { yv[v] = a.Y[node * NV + v]; sv[v] = a.dY[node * NV + v]; }
+    __shared__ double s_lo[NV], s_hi[NV], s_rt[NV];
+    if (threadIdx.x < NV) {
+        s_lo[threadIdx.x] = a.lo[threadIdx.x];
+        s_hi[threadIdx.x] = a.hi[threadIdx.x];
+        s_rt[threadIdx.x] = a.rtol[threadIdx.x];
+    }
+    __syncthreads();
+    const int64_t total = a.n_nodes * NV;
+    const int64_t right0 = (a.n_nodes - 1) * NV;  // first element of the last owned node
+    auto visit = [&](int64_t idx, double y, double s) {
+        if (s != s) nanf = 2.0;
+        const int v = (int)(idx % NV);  // NV is a compile-time constant: multiply-shift, no division
+        const bool pinned = (a.has_left && idx < NV && ((a.left_mask >> v) & 1ull)) ||
+                            (a.has_right && idx >= right0 && ((a.right_mask >> v) & 1ull));
+        if (pinned) return;
+        ss = fma(s, s, ss);
+        tol = fma(fabs(y), s_rt[v], tol);
+        const double nv_ = y + s;  // the reference evaluates y + step although it applies y - lambda*step
+        if (nv_ > s_hi[v]) fb = fmax(fmin(fb, (s_hi[v] - y) / (nv_ - y)), 0.0);
+        else if (nv_ < s_lo[v]) fb = fmin(fb, (y - s_lo[v]) / (y - nv_));
+    };
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    if constexpr (NV % 2 == 0) {  // fully coalesced 16-byte loads over the flat state
+        const double2 *y2 = reinterpret_cast<const double2 *>(a.Y);
+        const double2 *d2 = reinterpret_cast<const double2 *>(a.dY);
+        for (int64_t i2 = tid; i2 < total / 2; i2 += nthr) {
+            const double2 yy = y2[i2], sv = d2[i2];
+            visit(2 * i2, yy.x, sv.x);
+            visit(2 * i2 + 1, yy.y, sv.y);
         }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            const double s = sv[v], y = yv[v];
-            if (s != s) nanf = 2.0;
-            if ((pinmask >> v) & 1ull) continue;
-            ss = fma(s, s, ss);
-            tol = fma(fabs(y), rt[v], tol);
-            const double nv_ = y + s;  // the reference evaluates y + step although it applies y - lambda*step
-            if (nv_ > hi[v]) fb = fmax(fmin(fb, (hi[v] - y) / (nv_ - y)), 0.0);
-            else if (nv_ < lo[v]) fb = fmin(fb, (y - lo[v]) / (y - nv_));
-        }
+    } else {
+        for (int64_t idx = tid; idx < total; idx += nthr) visit(idx, a.Y[idx], a.dY[idx]);
     }
     if (a.F) {
-        const int64_t nf = a.n_rows * a.nv;
-        for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nf;
-             idx += (int64_t)gridDim.x * blockDim.x) {
-            const double f = a.F[idx];
-            if (f != f) nanf = fmax(nanf, 1.0);
+        const int64_t nf = a.n_rows * NV;
+        if constexpr (NV % 2 == 0) {
+            const double2 *f2 = reinterpret_cast<const double2 *>(a.F);
+            for (int64_t i2 = tid; i2 < nf / 2; i2 += nthr) {
+                const double2 f = f2[i2];
+                if (f.x != f.x || f.y != f.y) nanf = fmax(nanf, 1.0);
+            }
+        } else {
+            for (int64_t idx = tid; idx < nf; idx += nthr) {
+                const double f = a.F[idx];
+                if (f != f) nanf = fmax(nanf, 1.0);
+            }
         }
     }
     __shared__ double sh[4][8];

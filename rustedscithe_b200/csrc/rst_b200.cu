@@ -19,6 +19,7 @@
 #include "abd2.cuh"
 #include "abd3.cuh"
 #include "tps.cuh"
+#include "btd.cuh"
 #include "assemble.cuh"
 #include "newton.cuh"
 #include "generated/generated_problems.cuh"
@@ -99,6 +100,8 @@ struct SolverVT {
     void (*residual)(const double *A, const double *B, const double *X, const double *rhs, double *out, int64_t n,
                      cudaStream_t);
     void (*reduce)(const ReduceArgs &, int blocks, cudaStream_t);
+    void (*top_general)(const double *C, const double *D, const double *g, const double *Ba, const double *ba, int na,
+                        const double *Bb, const double *bb, int nb, double *Z, unsigned *flags, cudaStream_t);
 };
 
 // kernel generation: "v1" = one panel row per lane + shuffle broadcast (abd.cuh), default "v2" = two rows per lane +
@@ -121,7 +124,7 @@ struct SolverImpl {
         return (unsigned)((nslabs + per_block - 1) / per_block);
     }
     static void factor(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
-        if constexpr (NV % 2 == 0) {
+        if constexpr (NV % 2 == 0 && NV <= 12) {
             if (kernel_generation() == 2) {
                 const unsigned blocks = grid_for(L.nslabs, NV);
                 if (ident_b) abd_factor2_kernel<NV, true><<<blocks, 128, 0, st>>>(L, flags);
@@ -129,7 +132,9 @@ struct SolverImpl {
                 return;
             }
             // REDUX with several sub-warp masks serialises per mask: generation 3 only where a slab spans >= 16 lanes
-            if (kernel_generation() == 3 && NV >= 6) {
+        }
+        if constexpr (NV % 2 == 0) {
+            if (kernel_generation() >= 2 && NV >= 6) {
                 const unsigned blocks = grid_for(L.nslabs, 2 * NV);
                 if (ident_b) abd_factor3_kernel<NV, true><<<blocks, 128, 0, st>>>(L, flags);
                 else abd_factor3_kernel<NV, false><<<blocks, 128, 0, st>>>(L, flags);
@@ -141,7 +146,7 @@ struct SolverImpl {
         else abd_factor_kernel<NV, false><<<blocks, 128, 0, st>>>(L, flags);
     }
     static void forward(const AbdLevel &L, cudaStream_t st) {
-        if constexpr (NV % 2 == 0) {
+        if constexpr (NV % 2 == 0 && NV <= 12) {
             if (kernel_generation() == 2) {
                 abd_forward2_kernel<NV><<<grid_for(L.nslabs, NV), 128, 0, st>>>(L);
                 return;
@@ -164,12 +169,18 @@ struct SolverImpl {
     static void reduce(const ReduceArgs &a, int blocks, cudaStream_t st) {
         newton_reduce_kernel<NV><<<blocks, 256, 0, st>>>(a);
     }
-    static SolverVT vt() { return SolverVT{NV, &factor, &forward, &backward, &top, &residual, &reduce}; }
+    static void top_general(const double *C, const double *D, const double *g, const double *Ba, const double *ba, int na,
+                            const double *Bb, const double *bb, int nb, double *Z, unsigned *flags, cudaStream_t st) {
+        abd_top_general_kernel<NV><<<1, 32, 0, st>>>(C, D, g, Ba, ba, na, Bb, bb, nb, Z, flags);
+    }
+    static SolverVT vt() { return SolverVT{NV, &factor, &forward, &backward, &top, &residual, &reduce, &top_general}; }
 };
 
 static bool solver_vt_for(int nv, SolverVT *out) {
     switch (nv) {
         case 2: *out = SolverImpl<2>::vt(); return true;
+        case 4: *out = SolverImpl<4>::vt(); return true;
+        case 16: *out = SolverImpl<16>::vt(); return true;
         case 6: *out = SolverImpl<6>::vt(); return true;
         case 8: *out = SolverImpl<8>::vt(); return true;
         case 12: *out = SolverImpl<12>::vt(); return true;
@@ -238,8 +249,8 @@ struct rst_b200_solver {
 
 static rst_b200_solver *g_bound = nullptr;  // handle behind the reference's handle-less AOT symbols
 
-template <class T>
-static int dev_alloc(rst_b200_solver *s, T **p, size_t count) {
+template <class H, class T>
+static int dev_alloc(H *s, T **p, size_t count) {
     void *q = nullptr;
     if (count == 0) count = 1;
     CUDA_TRY(cudaMalloc(&q, count * sizeof(T)));
@@ -260,7 +271,8 @@ static int default_slab(int64_t n, int requested) {
     return 8;
 }
 
-static int build_level(rst_b200_solver *s, LevelBuf *lv, int64_t n, int S, const double *A, const double *B,
+template <class H>
+static int build_level(H *s, LevelBuf *lv, int64_t n, int S, const double *A, const double *B,
                        const double *r, double *Z) {
     const int nv = s->nv;
     AbdLevel &k = lv->k;
@@ -1042,6 +1054,65 @@ extern "C" int rst_b200_newton_solve(rst_b200_solver *s, const rst_b200_newton_o
     return RST_B200_OK;
 }
 
+// ---- frozen-Jacobian Newton -----------------------------------------------------
+// NR_Damp_solver_frozen.rs:1035-1096 (iteration) and :1105-1148 (try_main_loop); strategies BVP_utils.rs:362-480.
+static bool frozen_recalc(const rst_b200_frozen_opts *o, bool have_jac, int m, double error, double error_old) {
+    const double *sp = o->strategy_params;
+    switch (o->strategy) {
+        case RST_B200_FROZEN_NAIVE: return true;
+        case RST_B200_FROZEN_FROZEN_NAIVE: return !have_jac;
+        case RST_B200_FROZEN_EVERY_M: return !have_jac || m > (int)sp[0];
+        case RST_B200_FROZEN_AT_HIGH_NORM: return error > sp[0];
+        case RST_B200_FROZEN_AT_LOW_SPEED: return sp[0] * error_old < error;
+        case RST_B200_FROZEN_COMPLEX: return (error > sp[1]) || (m > (int)sp[0]) || (sp[2] * error_old < error);
+        default: return true;
+    }
+}
+
+extern "C" int rst_b200_newton_frozen(rst_b200_solver *s, const rst_b200_frozen_opts *o, rst_b200_newton_stats *st) {
+    if (!s || !o || !st) return fail(RST_B200_ERR_INVALID, "null argument");
+    if (o->strategy < 0 || o->strategy > RST_B200_FROZEN_COMPLEX) return fail(RST_B200_ERR_INVALID, "unknown strategy");
+    std::memset(st, 0, sizeof(*st));
+    cudaEventRecord(s->ev[0], s->stream);
+    bool jac_recalc = true, have_jac = false;
+    int m = 0, it = 0, status = 0;
+    double error_old = 0.0;
+    rst_b200_scalars sc{};
+    while (it < o->max_iterations) {
+        st->iterations++;
+        if (jac_recalc) {  // F(y) and J(y) in one fused pass, then the (cached) factorisation
+            TRY(rst_b200_eval_jacobian(s, 0));
+            TRY(rst_b200_factor(s));
+            have_jac = true;
+            m = 0;
+            st->jac_recalcs++;
+            st->factorizations++;
+        } else {
+            m += 1;
+            TRY(rst_b200_eval_residual(s, 0));
+        }
+        TRY(rst_b200_solve(s));
+        st->linear_solves++;
+        TRY(rst_b200_reduce(s, 0, &sc));
+        TRY(check_scalars(sc));
+        TRY(rst_b200_make_trial(s, 1.0));  // y_new = y - delta
+        TRY(rst_b200_accept_trial(s));
+        const double error = std::sqrt(sc.sumsq_step);  // ||y_new - y||
+        jac_recalc = frozen_recalc(o, have_jac, m, error, error_old);
+        error_old = error;
+        st->last_s1 = error;
+        if (error < o->tolerance) { status = 1; break; }
+        it += 1;
+    }
+    cudaEventRecord(s->ev[1], s->stream);
+    cudaEventSynchronize(s->ev[1]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]);
+    st->ms_total = ms;
+    st->status = status;
+    return RST_B200_OK;
+}
+
 // ---- host-pointer drop-ins -----------------------------------------------------------------------
 extern "C" int rst_b200_solve_in_place(rst_b200_solver *s, double *rhs, size_t len) {
     if (!s || !rhs) return fail(RST_B200_ERR_INVALID, "null argument");
@@ -1155,4 +1226,183 @@ extern "C" int rustedscithe_aot_eval_jacobian_values(const double *args, size_t 
     if (cudaMemcpyAsync(out, s->d_stream_out, nnz * sizeof(double), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) return 0;
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) return 0;
     return 1;
+}
+
+// ================================================================================================
+// BlockTridiagonal drop-in: BlockTridiagonalLuConsistent::{new, factor_from,
+// solve_in_place, solve_multiple_in_place} (block_tridiagonal_lu_consistent.rs:28, :98-218) on the GPU.
+// ================================================================================================
+struct rst_b200_btd {
+    int bs = 0, nv = 0, device = 0;
+    int64_t nb = 0, nb_eff = 0, n_int = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    SolverVT sv{};
+    std::vector<void *> owned;
+    std::vector<LevelBuf> levels;
+    double *lower = nullptr, *diag = nullptr, *upper = nullptr;  // device copies, padded to nb_eff blocks
+    double *A = nullptr, *B = nullptr, *r = nullptr, *Z = nullptr;
+    double *Ba = nullptr, *Bb = nullptr, *ba = nullptr, *bb = nullptr;
+    double *top_rows = nullptr, *top_g = nullptr, *Ztop = nullptr;
+    double *b_dev = nullptr, *x_dev = nullptr;
+    unsigned *d_flags = nullptr;
+    bool factored = false;
+};
+
+extern "C" int rst_b200_btd_create(int64_t n_blocks, int block_size, int device, void *stream, rst_b200_btd **out) {
+    if (!out) return fail(RST_B200_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (n_blocks <= 0 || block_size <= 0) return fail(RST_B200_ERR_INVALID, "n_blocks and block_size must be positive");  // :29-31
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(RST_B200_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
+    rst_b200_btd *s = new rst_b200_btd();
+    s->bs = block_size;
+    s->nv = 2 * block_size;
+    if (!solver_vt_for(s->nv, &s->sv)) {
+        delete s;
+        return fail(RST_B200_ERR_UNSUPPORTED, "block size not compiled in (supported: 1, 2, 3, 4, 6, 8)");
+    }
+    s->device = device;
+    s->nb = n_blocks;
+    s->nb_eff = n_blocks < 3 ? 3 : n_blocks;  // padded with decoupled identity blocks
+    s->n_int = s->nb_eff - 2;
+    CUDA_TRY(cudaSetDevice(device));
+    if (stream) s->stream = (cudaStream_t)stream;
+    else {
+        if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail(RST_B200_ERR_CUDA, "stream"); }
+        s->own_stream = true;
+    }
+    const int bs = s->bs, nv = s->nv;
+    auto build = [&]() -> int {
+        const size_t bl = (size_t)bs * bs;
+        TRY(dev_alloc(s, &s->lower, (size_t)(s->nb_eff - 1) * bl));
+        TRY(dev_alloc(s, &s->upper, (size_t)(s->nb_eff - 1) * bl));
+        TRY(dev_alloc(s, &s->diag, (size_t)s->nb_eff * bl));
+        TRY(dev_alloc(s, &s->A, (size_t)s->n_int * nv * nv));
+        TRY(dev_alloc(s, &s->B, (size_t)s->n_int * nv * nv));
+        TRY(dev_alloc(s, &s->r, (size_t)s->n_int * nv));
+        TRY(dev_alloc(s, &s->Z, (size_t)(s->n_int + 1) * nv));
+        TRY(dev_alloc(s, &s->Ba, (size_t)bs * nv));
+        TRY(dev_alloc(s, &s->Bb, (size_t)bs * nv));
+        TRY(dev_alloc(s, &s->ba, (size_t)bs));
+        TRY(dev_alloc(s, &s->bb, (size_t)bs));
+        TRY(dev_alloc(s, &s->top_rows, (size_t)2 * nv * nv));
+        TRY(dev_alloc(s, &s->top_g, (size_t)nv));
+        TRY(dev_alloc(s, &s->Ztop, (size_t)2 * nv));
+        TRY(dev_alloc(s, &s->b_dev, (size_t)s->nb_eff * bs));
+        TRY(dev_alloc(s, &s->x_dev, (size_t)s->nb_eff * bs));
+        TRY(dev_alloc(s, &s->d_flags, (size_t)4));
+        int64_t ln = s->n_int;
+        const double *lA = s->A, *lB = s->B, *lr = s->r;
+        double *lZ = s->Z;
+        while (ln > 1) {
+            LevelBuf lv{};
+            TRY(build_level(s, &lv, ln, default_slab(ln, 0), lA, lB, lr, lZ));
+            const int64_t nn = lv.k.nslabs;
+            if (nn > 1) {
+                TRY(dev_alloc(s, &lv.k.A_next, (size_t)nn * nv * nv));
+                TRY(dev_alloc(s, &lv.k.B_next, (size_t)nn * nv * nv));
+                TRY(dev_alloc(s, &lv.k.r_next, (size_t)nn * nv));
+                double *zn = nullptr;
+                TRY(dev_alloc(s, &zn, (size_t)(nn + 1) * nv));
+                lv.k.Z_next = zn;
+            } else {
+                lv.k.A_next = s->top_rows;
+                lv.k.B_next = s->top_rows + nv * nv;
+                lv.k.r_next = s->top_g;
+                lv.k.Z_next = s->Ztop;
+            }
+            s->levels.push_back(lv);
+            lA = lv.k.A_next; lB = lv.k.B_next; lr = lv.k.r_next;
+            lZ = const_cast<double *>(lv.k.Z_next);
+            ln = nn;
+        }
+        return RST_B200_OK;
+    };
+    const int rc = build();
+    if (rc != RST_B200_OK) {
+        for (void *p : s->owned) cudaFree(p);
+        if (s->own_stream) cudaStreamDestroy(s->stream);
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return RST_B200_OK;
+}
+
+extern "C" void rst_b200_btd_destroy(rst_b200_btd *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    for (void *p : s->owned) cudaFree(p);
+    if (s->own_stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" int64_t rst_b200_btd_n(const rst_b200_btd *s) { return s ? s->nb * s->bs : 0; }
+
+// factor_from(&BlockTridiagonal): lower[k] = block (k+1, k), upper[k] = block (k, k+1), row-major bs x bs blocks
+extern "C" int rst_b200_btd_factor_from(rst_b200_btd *s, const double *lower, const double *diag, const double *upper) {
+    if (!s || !diag || (s->nb > 1 && (!lower || !upper))) return fail(RST_B200_ERR_INVALID, "null argument");
+    const size_t bl = (size_t)s->bs * s->bs;
+    const int bs = s->bs;
+    s->factored = false;
+    CUDA_TRY(cudaMemsetAsync(s->lower, 0, (size_t)(s->nb_eff - 1) * bl * sizeof(double), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->upper, 0, (size_t)(s->nb_eff - 1) * bl * sizeof(double), s->stream));
+    if (s->nb > 1) {
+        CUDA_TRY(cudaMemcpyAsync(s->lower, lower, (size_t)(s->nb - 1) * bl * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->upper, upper, (size_t)(s->nb - 1) * bl * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(s->diag, diag, (size_t)s->nb * bl * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (s->nb_eff > s->nb) {  // identity padding blocks
+        std::vector<double> eye((size_t)(s->nb_eff - s->nb) * bl, 0.0);
+        for (int64_t k = 0; k < s->nb_eff - s->nb; ++k)
+            for (int i = 0; i < bs; ++i) eye[k * bl + (size_t)i * bs + i] = 1.0;
+        CUDA_TRY(cudaMemcpyAsync(s->diag + s->nb * bl, eye.data(), eye.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    CUDA_TRY(cudaMemsetAsync(s->d_flags, 0, sizeof(unsigned), s->stream));
+    btd_embed_kernel<<<148 * 4, 128, 0, s->stream>>>(s->lower, s->diag, s->upper, s->A, s->B, s->n_int, bs);
+    btd_boundary_kernel<<<1, 128, 0, s->stream>>>(s->lower, s->diag, s->upper, s->Ba, s->Bb, s->nb_eff, bs);
+    for (auto &lv : s->levels) s->sv.factor(lv.k, false, s->d_flags, s->stream);
+    CUDA_TRY(cudaGetLastError());
+    unsigned fl = 0;
+    CUDA_TRY(cudaMemcpyAsync(&fl, s->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (fl & RST_FLAG_ZERO_PIVOT) return fail(RST_B200_ERR_ZERO_PIVOT, "zero pivot: the block-tridiagonal matrix is singular");
+    s->factored = true;
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_btd_solve_in_place(rst_b200_btd *s, double *rhs, size_t len) {
+    if (!s || !rhs) return fail(RST_B200_ERR_INVALID, "null argument");
+    if (!s->factored) return fail(RST_B200_ERR_NOT_FACTORIZED, "solve before factor");                 // BandedError::NotFactorized
+    if ((int64_t)len != s->nb * s->bs) return fail(RST_B200_ERR_INVALID, "rhs length mismatch");       // DimensionMismatch
+    const int nv = s->nv, bs = s->bs;
+    CUDA_TRY(cudaMemsetAsync(s->b_dev, 0, (size_t)s->nb_eff * bs * sizeof(double), s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->b_dev, rhs, len * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    btd_rhs_kernel<<<148 * 2, 128, 0, s->stream>>>(s->b_dev, s->r, s->ba, s->bb, s->nb_eff, bs);
+    for (auto &lv : s->levels) s->sv.forward(lv.k, s->stream);
+    const bool single = s->levels.empty();
+    const double *C = single ? s->A : s->top_rows, *D = single ? s->B : s->top_rows + nv * nv, *g = single ? s->r : s->top_g;
+    s->sv.top_general(C, D, g, s->Ba, s->ba, bs, s->Bb, s->bb, bs, single ? s->Z : s->Ztop, s->d_flags, s->stream);
+    for (int i = (int)s->levels.size() - 1; i >= 0; --i) s->sv.backward(s->levels[i].k, s->stream);
+    btd_extract_kernel<<<148 * 2, 128, 0, s->stream>>>(s->Z, s->x_dev, s->nb_eff, bs);
+    CUDA_TRY(cudaGetLastError());
+    unsigned fl = 0;
+    CUDA_TRY(cudaMemcpyAsync(rhs, s->x_dev, len * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(&fl, s->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (fl & RST_FLAG_ZERO_PIVOT) return fail(RST_B200_ERR_ZERO_PIVOT, "zero pivot: the block-tridiagonal matrix is singular");
+    return RST_B200_OK;
+}
+
+// column-major multi-RHS with leading dimension ldb >= n (block_tridiagonal_lu_consistent.rs:220-247)
+extern "C" int rst_b200_btd_solve_multiple_in_place(rst_b200_btd *s, double *rhs, size_t nrhs, size_t ldb) {
+    if (!s || !rhs) return fail(RST_B200_ERR_INVALID, "null argument");
+    const size_t n = (size_t)(s->nb * s->bs);
+    if (ldb < n) return fail(RST_B200_ERR_INVALID, "ldb < n");  // BandedError::InvalidRhsLayout
+    for (size_t c = 0; c < nrhs; ++c) TRY(rst_b200_btd_solve_in_place(s, rhs + c * ldb, n));
+    return RST_B200_OK;
 }

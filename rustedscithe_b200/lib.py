@@ -43,6 +43,14 @@ class NewtonStats(C.Structure):
                 ("ms_total", C.c_double)]
 
 
+class FrozenOpts(C.Structure):
+    _fields_ = [("strategy", C.c_int), ("strategy_params", C.c_double * 3), ("tolerance", C.c_double),
+                ("max_iterations", C.c_int)]
+
+
+FROZEN_STRATEGIES = {"Naive": 0, "Frozen_naive": 1, "every_m": 2, "at_high_morm": 3, "at_low_speed": 4, "complex": 5}
+
+
 class Scalars(C.Structure):
     _fields_ = [("sumsq_step", C.c_double), ("tol_sum", C.c_double), ("fbound", C.c_double),
                 ("nan_flag", C.c_double), ("device_flags", C.c_double)]
@@ -78,6 +86,7 @@ SYMBOLS = {
     "rst_b200_checkpoint": (C.c_int, [_H, C.c_int]),
     "rst_b200_newton_solve": (C.c_int, [_H, C.POINTER(NewtonOpts), C.POINTER(NewtonStats)]),
     "rst_b200_newton_iterate": (C.c_int, [_H, C.POINTER(NewtonOpts), C.c_int, C.POINTER(NewtonStats)]),
+    "rst_b200_newton_frozen": (C.c_int, [_H, C.POINTER(FrozenOpts), C.POINTER(NewtonStats)]),
     "rst_b200_solve_in_place": (C.c_int, [_H, c_f64_p, C.c_size_t]),
     "rst_b200_solve_multiple_in_place": (C.c_int, [_H, c_f64_p, C.c_size_t, C.c_size_t]),
     "rst_b200_jacobian_structure": (C.c_int64, [_H, c_i64_p, c_i64_p, c_i64_p, c_i64_p, c_int_p, c_int_p]),
@@ -92,6 +101,12 @@ SYMBOLS = {
     "rst_b200_solve_reduced_backward": (C.c_int, [_H]),
     "rst_b200_reduce_local": (C.c_int, [_H, C.c_int]),
     "rst_b200_reduce_finish": (C.c_int, [_H, C.POINTER(Scalars)]),
+    "rst_b200_btd_create": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.POINTER(_H)]),
+    "rst_b200_btd_destroy": (None, [_H]),
+    "rst_b200_btd_n": (C.c_int64, [_H]),
+    "rst_b200_btd_factor_from": (C.c_int, [_H, c_f64_p, c_f64_p, c_f64_p]),
+    "rst_b200_btd_solve_in_place": (C.c_int, [_H, c_f64_p, C.c_size_t]),
+    "rst_b200_btd_solve_multiple_in_place": (C.c_int, [_H, c_f64_p, C.c_size_t, C.c_size_t]),
     "rst_b200_memcpy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "rst_b200_launch_count": (C.c_int64, [_H]),
 }

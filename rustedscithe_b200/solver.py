@@ -166,6 +166,17 @@ class NRBVP:
         self.result = self.get_state() if self.stats.status == 1 else None
         return self.result
 
+    def try_solve_frozen(self, strategy="Frozen_naive", strategy_params=(), tolerance=1e-6, max_iterations=25):
+        """Frozen-Jacobian Newton (NR_Damp_solver_frozen.rs: NRBVP::try_solve with FrozenSolverOptions)."""
+        o = _lib.FrozenOpts()
+        o.strategy = _lib.FROZEN_STRATEGIES[strategy]
+        for i, v in enumerate(strategy_params):
+            o.strategy_params[i] = float(v)
+        o.tolerance, o.max_iterations = tolerance, max_iterations
+        _lib.check(self.L.rst_b200_newton_frozen(self.handle, C.byref(o), C.byref(self.stats)))
+        self.result = self.get_state() if self.stats.status == 1 else None
+        return self.result
+
     def newton_iterate(self, recalc_jacobian=True):
         opts = self._opts()
         _lib.check(self.L.rst_b200_newton_iterate(self.handle, C.byref(opts), 1 if recalc_jacobian else 0,
@@ -263,3 +274,45 @@ class NRBVP:
                 return 1
         self._allgather_cb = _lib.ALLGATHER_FN(tramp)
         _lib.check(self.L.rst_b200_set_allgather(self.handle, self._allgather_cb, None))
+
+
+class BlockTridiagonalLu:
+    """GPU drop-in for BlockTridiagonalLuConsistent (src/somelinalg/banded/block_tridiagonal_lu_consistent.rs:28,
+    :98-247): ``new(n_blocks, block_size)`` -> ``factor_from(lower, diag, upper)`` -> ``solve_in_place(rhs)``."""
+
+    def __init__(self, n_blocks, block_size, device=0, stream=None):
+        self.L = _lib.load()
+        self.n_blocks, self.block_size = int(n_blocks), int(block_size)
+        self.handle = C.c_void_p()
+        _lib.check(self.L.rst_b200_btd_create(self.n_blocks, self.block_size, device, stream, C.byref(self.handle)))
+
+    def n(self):
+        return int(self.L.rst_b200_btd_n(self.handle))
+
+    def factor_from(self, lower, diag, upper):
+        nb, bs = self.n_blocks, self.block_size
+        diag = _f64(diag).reshape(nb, bs, bs)
+        lower = _f64(lower).reshape(max(nb - 1, 0), bs, bs) if nb > 1 else np.zeros((1, bs, bs))
+        upper = _f64(upper).reshape(max(nb - 1, 0), bs, bs) if nb > 1 else np.zeros((1, bs, bs))
+        _lib.check(self.L.rst_b200_btd_factor_from(self.handle, _p(lower), _p(diag), _p(upper)))
+
+    def solve_in_place(self, rhs):
+        x = _f64(rhs).copy()
+        _lib.check(self.L.rst_b200_btd_solve_in_place(self.handle, _p(x), x.shape[0]))
+        return x
+
+    def solve_multiple_in_place(self, rhs, nrhs, ldb):
+        x = _f64(rhs).copy()
+        _lib.check(self.L.rst_b200_btd_solve_multiple_in_place(self.handle, _p(x), nrhs, ldb))
+        return x
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.L.rst_b200_btd_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -22,7 +22,7 @@
 #include "btd.cuh"
 #include "assemble.cuh"
 #include "newton.cuh"
-#include "generated/generated_problems.cuh"
+#include "generated_problems.cuh"  // from the -I generated directory (default: csrc/generated)
 
 using namespace rst;
 
@@ -75,7 +75,7 @@ static void launch_assemble(const AsmArgs &a, bool with_j, bool trap, cudaStream
 
 static const ProblemVT g_problems[] = {
 #define RST_PROBLEM(P, H) {P::key(), P::NV, P::NP, H, P::pattern(), &launch_assemble<P>},
-#include "generated/generated_registry.inc"
+#include "generated_registry.inc"
 #undef RST_PROBLEM
 };
 static const int g_nproblems = (int)(sizeof(g_problems) / sizeof(g_problems[0]));
@@ -178,12 +178,9 @@ struct SolverImpl {
 
 static bool solver_vt_for(int nv, SolverVT *out) {
     switch (nv) {
-        case 2: *out = SolverImpl<2>::vt(); return true;
-        case 4: *out = SolverImpl<4>::vt(); return true;
-        case 16: *out = SolverImpl<16>::vt(); return true;
-        case 6: *out = SolverImpl<6>::vt(); return true;
-        case 8: *out = SolverImpl<8>::vt(); return true;
-        case 12: *out = SolverImpl<12>::vt(); return true;
+#define RST_NV(n) case n: *out = SolverImpl<n>::vt(); return true;
+#include "generated_nv_list.inc"  // block sizes of the compiled-in problems + the BlockTridiagonal drop-in sizes
+#undef RST_NV
         default: return false;
     }
 }

@@ -111,7 +111,7 @@ SYMBOLS = {
     "rst_b200_launch_count": (C.c_int64, [_H]),
 }
 
-_lib = None
+_libs = {}
 
 
 class RstB200Error(RuntimeError):
@@ -120,24 +120,28 @@ class RstB200Error(RuntimeError):
         self.code = code
 
 
-def load():
-    """dlopen the library and bind every declared symbol.  Raises if it has not been built."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def load(path: str | None = None):
+    """dlopen a library and bind every declared symbol.  Raises if it has not been built."""
+    path = os.path.abspath(path or LIB_PATH)
+    if path not in _libs:
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `python -m rustedscithe_b200.build` "
+                f"{path} is missing: build it with `python -m rustedscithe_b200.build` "
                 "(there is no CPU fallback for the B200 path)")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        _lib = L
-    return _lib
+        _libs[path] = L
+    return _libs[path]
 
 
-def check(rc):
+def has_problem(L, key: str) -> bool:
+    return any(L.rst_b200_problem_key(i) == key.encode() for i in range(L.rst_b200_problem_count()))
+
+
+def check(rc, L=None):
     if rc != OK:
-        raise RstB200Error(rc, (load().rst_b200_last_error() or b"").decode())
+        raise RstB200Error(rc, ((L or load()).rst_b200_last_error() or b"").decode())
     return rc

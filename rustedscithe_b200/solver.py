@@ -59,12 +59,18 @@ class NRBVP:
     """Damped Newton BVP solver bound to one compiled-in AOT problem (device-resident state)."""
 
     def __init__(self, problem, initial_guess, n_steps, options: DampedSolverOptions | None = None,
-                 t0=None, t_end=None, mesh=None, boundary_conditions=None, params=None):
+                 t0=None, t_end=None, mesh=None, boundary_conditions=None, params=None,
+                 aot_build_policy="build_if_missing"):
         self.spec = _problems.get(problem) if isinstance(problem, str) else problem
         spec = self.spec
         self.options = options or DampedSolverOptions.from_spec(spec)
         o = self.options
         self.L = _lib.load()
+        if not _lib.has_problem(self.L, spec.key):
+            # AOT lifecycle (generated_solver_handoff.rs:321-331): a problem outside the default library gets its
+            # own artefact, built once (BuildIfMissing) or required to exist (RequirePrebuilt)
+            from . import build as _build
+            self.L = _lib.load(_build.build_artifact(spec, aot_build_policy))
         self.nv = spec.nv
         self.n_steps = int(n_steps)
         self.n = self.nv * self.n_steps
@@ -109,7 +115,7 @@ class NRBVP:
         d.slab = o.slab
         d.rank, d.world = o.rank, o.world
         self.handle = C.c_void_p()
-        _lib.check(self.L.rst_b200_create(C.byref(d), C.byref(self.handle)))
+        self._ck(self.L.rst_b200_create(C.byref(d), C.byref(self.handle)))
         self.stats = _lib.NewtonStats()
         self.result = None
         self._allgather_cb = None
@@ -119,6 +125,9 @@ class NRBVP:
             if g.ndim == 2:
                 g = g.reshape(-1, order="F")
             self.set_state(g)
+
+    def _ck(self, rc):
+        return _lib.check(rc, self.L)
 
     @classmethod
     def new_with_options(cls, problem, initial_guess, n_steps, options=None, **kw):
@@ -138,16 +147,16 @@ class NRBVP:
     # -- state ---------------------------------------------------------------------------------
     def set_state(self, y_reduced):
         y = _f64(y_reduced)
-        _lib.check(self.L.rst_b200_set_state(self.handle, _p(y), y.shape[0]))
+        self._ck(self.L.rst_b200_set_state(self.handle, _p(y), y.shape[0]))
 
     def get_state(self):
         y = np.zeros(self.n)
-        _lib.check(self.L.rst_b200_get_state(self.handle, _p(y), y.shape[0]))
+        self._ck(self.L.rst_b200_get_state(self.handle, _p(y), y.shape[0]))
         return y
 
     def set_params(self, params):
         p = _f64(params)
-        _lib.check(self.L.rst_b200_set_params(self.handle, _p(p), p.shape[0]))
+        self._ck(self.L.rst_b200_set_params(self.handle, _p(p), p.shape[0]))
 
     def device_ptr(self, which):
         return self.L.rst_b200_device_ptr(self.handle, which)
@@ -173,20 +182,20 @@ class NRBVP:
         for i, v in enumerate(strategy_params):
             o.strategy_params[i] = float(v)
         o.tolerance, o.max_iterations = tolerance, max_iterations
-        _lib.check(self.L.rst_b200_newton_frozen(self.handle, C.byref(o), C.byref(self.stats)))
+        self._ck(self.L.rst_b200_newton_frozen(self.handle, C.byref(o), C.byref(self.stats)))
         self.result = self.get_state() if self.stats.status == 1 else None
         return self.result
 
     def newton_iterate(self, recalc_jacobian=True):
         opts = self._opts()
-        _lib.check(self.L.rst_b200_newton_iterate(self.handle, C.byref(opts), 1 if recalc_jacobian else 0,
+        self._ck(self.L.rst_b200_newton_iterate(self.handle, C.byref(opts), 1 if recalc_jacobian else 0,
                                                   C.byref(self.stats)))
         return self.stats.status
 
     def get_result(self):
         """(N+1) x nv matrix with boundary values re-inserted (NR_Damp_solver_damped.rs:2540-2558)."""
         full = np.zeros((self.n_steps + 1) * self.nv)
-        _lib.check(self.L.rst_b200_get_full_solution(self.handle, _p(full), full.shape[0]))
+        self._ck(self.L.rst_b200_get_full_solution(self.handle, _p(full), full.shape[0]))
         return full.reshape(self.n_steps + 1, self.nv)
 
     def get_statistics(self):
@@ -227,38 +236,38 @@ class NRBVP:
 
     # -- DirectLinearSolver surface ---------------------------------------------------------
     def factor(self):
-        _lib.check(self.L.rst_b200_factor(self.handle))
+        self._ck(self.L.rst_b200_factor(self.handle))
 
     def solve_in_place(self, rhs):
         x = _f64(rhs).copy()
-        _lib.check(self.L.rst_b200_solve_in_place(self.handle, _p(x), x.shape[0]))
+        self._ck(self.L.rst_b200_solve_in_place(self.handle, _p(x), x.shape[0]))
         return x
 
     def solve_multiple_in_place(self, rhs, nrhs, ldb):
         x = _f64(rhs).copy()
-        _lib.check(self.L.rst_b200_solve_multiple_in_place(self.handle, _p(x), nrhs, ldb))
+        self._ck(self.L.rst_b200_solve_multiple_in_place(self.handle, _p(x), nrhs, ldb))
         return x
 
     # -- device-resident primitives ------------------------------------------------------------
     def eval_residual(self, which=0):
-        _lib.check(self.L.rst_b200_eval_residual(self.handle, which))
+        self._ck(self.L.rst_b200_eval_residual(self.handle, which))
 
     def eval_jacobian(self, which=0):
-        _lib.check(self.L.rst_b200_eval_jacobian(self.handle, which))
+        self._ck(self.L.rst_b200_eval_jacobian(self.handle, which))
 
     def solve(self):
-        _lib.check(self.L.rst_b200_solve(self.handle))
+        self._ck(self.L.rst_b200_solve(self.handle))
 
     def reduce(self, which=0):
         sc = _lib.Scalars()
-        _lib.check(self.L.rst_b200_reduce(self.handle, which, C.byref(sc)))
+        self._ck(self.L.rst_b200_reduce(self.handle, which, C.byref(sc)))
         return sc
 
     def checkpoint(self, restore=False):
-        _lib.check(self.L.rst_b200_checkpoint(self.handle, 1 if restore else 0))
+        self._ck(self.L.rst_b200_checkpoint(self.handle, 1 if restore else 0))
 
     def sync(self):
-        _lib.check(self.L.rst_b200_sync(self.handle))
+        self._ck(self.L.rst_b200_sync(self.handle))
 
     def launch_count(self):
         return int(self.L.rst_b200_launch_count(self.handle))
@@ -273,7 +282,7 @@ class NRBVP:
                 traceback.print_exc()
                 return 1
         self._allgather_cb = _lib.ALLGATHER_FN(tramp)
-        _lib.check(self.L.rst_b200_set_allgather(self.handle, self._allgather_cb, None))
+        self._ck(self.L.rst_b200_set_allgather(self.handle, self._allgather_cb, None))
 
 
 class BlockTridiagonalLu:

@@ -212,6 +212,8 @@ struct rst_b200_solver {
     // device buffers
     double *Y = nullptr, *Yt = nullptr, *F = nullptr, *A = nullptr, *B = nullptr, *dY = nullptr;
     double *d_mesh = nullptr, *d_params = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_rtol = nullptr;
+    double *dY1 = nullptr;    // step of a damping trial (the undamped step in dY must survive rejected trials)
+    double *sol = nullptr;    // buffer the linear solve currently writes to (dY or dY1)
     double *Ysave = nullptr;  // device-side checkpoint of Y (rst_b200_checkpoint)
     double *d_tmp = nullptr;  // [n*nv + nv] staging for reduced-order host drop-ins
     std::vector<void *> owned;
@@ -390,6 +392,8 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
         TRY(dev_alloc(s, &s->Y, nodes));
         TRY(dev_alloc(s, &s->Yt, nodes));
         TRY(dev_alloc(s, &s->dY, nodes));
+        TRY(dev_alloc(s, &s->dY1, nodes));
+        s->sol = s->dY;
         TRY(dev_alloc(s, &s->F, (size_t)n * nv));
         TRY(dev_alloc(s, &s->A, (size_t)n * nv * nv));
         if (s->scheme == RST_B200_SCHEME_TRAPEZOID) TRY(dev_alloc(s, &s->B, (size_t)n * nv * nv));
@@ -403,6 +407,7 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
         CUDA_TRY(cudaMemsetAsync(s->Y, 0, nodes * sizeof(double), s->stream));
         CUDA_TRY(cudaMemsetAsync(s->Yt, 0, nodes * sizeof(double), s->stream));
         CUDA_TRY(cudaMemsetAsync(s->dY, 0, nodes * sizeof(double), s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->dY1, 0, nodes * sizeof(double), s->stream));
         if (s->np > 0) CUDA_TRY(cudaMemcpyAsync(s->d_params, d->params, s->np * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(cudaMemcpyAsync(s->d_lo, d->lo, nv * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(cudaMemcpyAsync(s->d_hi, d->hi, nv * sizeof(double), cudaMemcpyHostToDevice, s->stream));
@@ -867,7 +872,7 @@ extern "C" int rst_b200_reduce_local(rst_b200_solver *s, int which_state) {
     if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
     ReduceArgs a{};
     a.Y = which_state ? s->Yt : s->Y;
-    a.dY = s->dY;
+    a.dY = s->sol;
     a.F = s->F;
     a.lo = s->d_lo; a.hi = s->d_hi; a.rtol = s->d_rtol;
     // ranks own nodes [0, n) of their slab; the last rank also owns global node N
@@ -939,6 +944,17 @@ extern "C" int rst_b200_checkpoint(rst_b200_solver *s, int restore) {
     return RST_B200_OK;
 }
 
+// the level-0 node values ARE the solution of the linear solve: redirect them to `buf`
+static void set_solution_buffer(rst_b200_solver *s, double *buf) {
+    s->sol = buf;
+    if (s->use_tps) {
+        if (!s->tps_big.empty()) s->tps_big[0].Z = buf;
+        else s->tps_tail.lv[0].Z = buf;
+    } else if (!s->levels.empty()) {
+        s->levels[0].k.Z = buf;
+    }
+}
+
 // ---- damped Newton -------------------------------------------------------------------------------
 static int check_scalars(const rst_b200_scalars &sc) {
     if (sc.nan_flag != 0.0) return fail(RST_B200_ERR_NAN, "NaN in residual or Newton step");
@@ -978,6 +994,12 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
     int k = 0;
     bool accepted = false;
     double s1 = 0.0, conv = 0.0;
+    // trial steps go to dY1: the undamped step in dY is re-used by every damping trial (:1934, :1971)
+    struct Restore {
+        rst_b200_solver *s;
+        ~Restore() { set_solution_buffer(s, s->dY); }
+    } restore{s};
+    set_solution_buffer(s, s->dY1);
     while (k < o->max_damp_iter) {
         TRY(rst_b200_make_trial(s, lambda));
         TRY(newton_step(s, 1, st));

@@ -217,6 +217,30 @@ def test_bound_violation_status_matches_oracle():
     g.close()
 
 
+@pytest.mark.parametrize("key,n_steps,scale", [("coupled8", 300, 0.8), ("damp1", 400, -4.0), ("coupled8", 80, 0.5),
+                                               ("damp1", 400, 3.5), ("combustion6", 2000, 0.8)])
+def test_rejected_damping_trials_follow_the_reference(key, n_steps, scale):
+    """Starts that force REJECTED damping trials (more than two linear solves in an iteration,
+    NR_Damp_solver_damped.rs:1927-1976: every trial re-uses the undamped step with a smaller lambda) and failure
+    statuses: counters, status and -- when it converges -- the solution must follow the oracle."""
+    spec = problems.get(key)
+    o = _oracle(key, n_steps)
+    y0 = np.full(o.n, scale)
+    lo, hi = spec.bounds_per_var()
+    ref = o.newton(y0, o.per_unknown(lo), o.per_unknown(hi), o.per_unknown(spec.rtol_per_var()), abs_tol=spec.abs_tol,
+                   max_iterations=spec.max_iterations, max_jac=spec.max_jac, max_damp_iter=spec.max_damp_iter,
+                   damp_factor=spec.damp_factor)
+    g = _gpu(key, n_steps, guess=y0)
+    sol = g.try_solve()
+    st = g.get_statistics()
+    assert st["status"] == ref.status
+    assert (st["number of iterations"], st["number of solving linear systems"],
+            st["number of jacobians recalculations"]) == (ref.iterations, ref.linear_solves, ref.jac_recalcs)
+    if ref.status == 1:
+        assert np.max(np.abs(sol - ref.y) / np.maximum(1.0, np.abs(ref.y))) < TOL_SOL
+    g.close()
+
+
 # ---- BASELINE.json full sizes: size-independent properties ------------------------------------------
 def test_config_c2_million_points_closed_form_and_idempotence():
     """C2: 2-variable BVP at 10^6 points.  The discrete solution of y'=z, z'=0, y(0)=0, z(1)=1 is y = x, z = 1

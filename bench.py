@@ -170,6 +170,9 @@ def main():
     ap.add_argument("--cpu-points", type=int, default=0, help="mesh size of the CPU sample (default per workload)")
     ap.add_argument("--slab", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl-exchange", action="store_true",
+                    help="move the interface rows with torch.distributed/NCCL through the host callback instead of the "
+                         "NVLink peer-memory kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,10 +210,20 @@ def main():
                                              world=world, slab=args.slab)
         y0 = spec.guess(n_global)
         solver = NRBVP(key, y0, n_global, opts)
-        if world > 1:
+        if world > 1 and not args.nccl_exchange:
+            # NVLink peer-memory mailboxes: exchange the IPC handles once, then the library gathers on its own stream
+            handles = [None] * world
+            dist.all_gather_object(handles, solver.p2p_handle())
+            solver.p2p_open(handles)
+        elif world > 1:
+            views = {}   # the library's exchange buffers have fixed addresses: wrap each of them once
+
             def allgather(send, recv, count, _stream):
-                s = torch.as_tensor(RawCuda(send, count), device="cuda")
-                r = torch.as_tensor(RawCuda(recv, count * world), device="cuda")
+                key_ = (send, recv, count)
+                if key_ not in views:
+                    views[key_] = (torch.as_tensor(RawCuda(send, count), device="cuda"),
+                                   torch.as_tensor(RawCuda(recv, count * world), device="cuda"))
+                s, r = views[key_]
                 dist.all_gather_into_tensor(r, s)
                 return 0
             solver.set_allgather(allgather)
@@ -370,6 +383,8 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"{args.workload}: {desc}", "problem": key, "nv": nv, "points_per_gpu": n_local,
                            "points_total": n_global, "parallelism": f"mesh-slab x{world}",
+                           "interface_exchange": ("none" if world == 1 else ("nccl all_gather via host callback" if args.nccl_exchange
+                                                                             else "NVLink peer-memory mailbox kernel (CUDA IPC)")),
                            "l2_policy": "working set per step (state + blocks + factors) exceeds the 126 MB L2"
                                         if n_local * nv * nv * 8 * 6 > 126e6 else "working set smaller than L2 (C1)",
                            "step": "one complete damped Newton solve from the initial guess (device checkpoint restore); "

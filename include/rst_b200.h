@@ -180,6 +180,11 @@ int rustedscithe_aot_eval_jacobian_values(const double *args, size_t args_len, d
 typedef int (*rst_b200_allgather_fn)(void *ctx, const void *d_send, void *d_recv, int64_t doubles_per_rank,
                                      void *stream);
 int rst_b200_set_allgather(rst_b200_solver *s, rst_b200_allgather_fn fn, void *ctx);
+/* NVLink peer-memory exchange (preferred): every rank exports the CUDA IPC handle of its mailbox (64 bytes), the host
+ * application all-gathers the handles once (any transport) and hands the array back; from then on rst_b200_factor /
+ * _solve / _reduce run the all-gather as a small kernel on the solver's own stream -- no host callback, no NCCL. */
+int rst_b200_p2p_get_handle(rst_b200_solver *s, void *handle_out, size_t handle_bytes);
+int rst_b200_p2p_open(rst_b200_solver *s, const void *handles /* [world][handle_stride] */, size_t handle_stride);
 /* local intervals [begin, end) of this rank */
 int rst_b200_dist_range(const rst_b200_solver *s, int64_t *j_begin, int64_t *j_end);
 /* phase-split primitives (rst_b200_factor / _solve / _reduce call them around the all-gather callback;

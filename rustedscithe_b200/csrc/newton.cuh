@@ -12,6 +12,7 @@
 // pinned components of node 0 / node N so reductions run over the reference's unknowns only.
 #pragma once
 #include "rst_common.cuh"
+#include "p2p.cuh"
 
 namespace rst {
 
@@ -109,9 +110,11 @@ __global__ void __launch_bounds__(256) newton_reduce_kernel(ReduceArgs a) {
     }
 }
 
-// deterministic second stage: out[0..3] = {sumsq, tolsum, fbound, nanflag}; out[4] = device error flags
+// deterministic second stage: out[0..3] = {sumsq, tolsum, fbound, nanflag}; out[4] = device error flags.
+// Multi-GPU with mapped peers: the 8-scalar all-gather over NVLink and the combination run in the same launch.
 __global__ void __launch_bounds__(256) newton_reduce_final_kernel(const double *partials, int nblocks, double *out,
-                                                                  const unsigned *flags) {
+                                                                  unsigned *flags, P2pPeers peers, int rank, int world,
+                                                                  int pay, unsigned long long seq, double *gscal) {
     double a0 = 0.0, a1 = 0.0, a2 = 1.0, a3 = 0.0;
     for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
         a0 += partials[4 * i]; a1 += partials[4 * i + 1];
@@ -129,6 +132,19 @@ __global__ void __launch_bounds__(256) newton_reduce_final_kernel(const double *
         }
         out[0] = b0; out[1] = b1; out[2] = b2; out[3] = b3;
         out[4] = (double)(*flags);
+        out[5] = 0.0; out[6] = 0.0; out[7] = 0.0;
+    }
+    if (world > 1) {
+        p2p_allgather_block(peers, out, 8, gscal, rank, world, pay, seq, flags);
+        if (threadIdx.x == 0) {
+            double c0 = 0.0, c1 = 0.0, c2 = 1.0, c3 = 0.0, c4 = 0.0;
+            for (int p = 0; p < world; ++p) {
+                c0 += gscal[8 * p]; c1 += gscal[8 * p + 1]; c2 = fmin(c2, gscal[8 * p + 2]);
+                c3 = fmax(c3, gscal[8 * p + 3]); c4 = fmax(c4, gscal[8 * p + 4]);
+            }
+            out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+            out[4] = fmax(c4, (double)(*flags));
+        }
     }
 }
 

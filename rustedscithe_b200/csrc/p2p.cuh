@@ -1,0 +1,188 @@
+// p2p.cuh -- latency-bound all-gather of the mesh-slab interface data over NVLink peer memory.
+//
+// The only data-path exchange of the multi-GPU path is an all-gather of a few hundred
+// doubles per rank: the condensed interface row (2 nv^2) per factorisation, its right-hand side (nv) per solve and
+// 8 damping scalars per trial.  Through NCCL + a host callback each of them costs ~25 us of launch/host latency,
+// which is a quarter of a 1 ms Newton solve at C2.  Here every rank owns a "mailbox" in its HBM that its peers map
+// through CUDA IPC; the gather is ONE small kernel per rank on the solver's own stream:
+//   1. store my payload into slot [parity][my_rank] of every peer's mailbox (peer stores travel over NVLink),
+//   2. __threadfence_system(), then release-store the sequence number into the peers' flag words,
+//   3. acquire-spin on my own flag words until every peer's sequence number has arrived,
+//   4. copy my mailbox (L1 bypassed) into the local gather buffer.
+// One process per GPU, so the kernels of different ranks always run concurrently (each on its own device); slots are
+// double-buffered by the parity of the sequence number: a rank cannot run two gathers ahead of a peer because it
+// waits for that peer's flag of the gather in between.
+#pragma once
+#include "rst_common.cuh"
+
+namespace rst {
+
+constexpr int P2P_MAX_WORLD = 16;
+
+struct P2pPeers {
+    double *mailbox[P2P_MAX_WORLD];  // peer mailboxes (own entry = local pointer)
+};
+
+// mailbox layout: payload[2][world][pay] doubles, then flags[2][world] unsigned long long
+__host__ __device__ inline size_t p2p_mailbox_doubles(int world, int pay) { return (size_t)2 * world * pay + (size_t)2 * world; }
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// The gather as a block-wide device function (every thread of ONE CTA calls it): used stand-alone below and fused into
+// the single-CTA tail / reduction kernels so a multi-GPU solve needs no extra launches.
+__device__ __forceinline__ void p2p_allgather_block(const P2pPeers &peers, const double *send, int count, double *recv,
+                                                    int my_rank, int world, int pay, unsigned long long seq,
+                                                    unsigned *flags) {
+    const int parity = (int)(seq & 1ull);
+    const size_t slot = ((size_t)parity * world + my_rank) * pay;
+    const size_t flag_base = (size_t)2 * world * pay;
+    __syncthreads();  // `send` may have been produced by other threads of this CTA
+    for (int p = 0; p < world; ++p) {
+        double *dst = peers.mailbox[p] + slot;
+        for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = send[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        unsigned long long *pf = reinterpret_cast<unsigned long long *>(peers.mailbox[threadIdx.x] + flag_base) +
+                                 (size_t)parity * world + my_rank;
+        st_release_sys(pf, seq);
+        const unsigned long long *mf = reinterpret_cast<const unsigned long long *>(peers.mailbox[my_rank] + flag_base) +
+                                       (size_t)parity * world + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(mf) < seq) {
+            if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer never arrived
+                atomicOr(flags, RST_FLAG_PEER_TIMEOUT);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const double *mine = peers.mailbox[my_rank] + (size_t)parity * world * pay;
+    for (int idx = threadIdx.x; idx < world * count; idx += blockDim.x) {
+        const int p = idx / count, i = idx - p * count;
+        recv[idx] = __ldcg(mine + (size_t)p * pay + i);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) p2p_allgather_kernel(P2pPeers peers, const double *__restrict__ send, int count,
+                                                            double *__restrict__ recv, int my_rank, int world, int pay,
+                                                            unsigned long long seq, unsigned *flags) {
+    p2p_allgather_block(peers, send, count, recv, my_rank, world, pay, seq, flags);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Interface system of the mesh-slab partition, solved redundantly on every rank INSIDE the single-CTA kernels:
+//   C_p Z_p + D_p Z_{p+1} = g_p (p = 0..world-1, nv rows each)  +  nv pinned boundary components of Z_0 / Z_world.
+// Dense (world+1) nv square system: LU with partial pivoting at factor time, substitution per right-hand side.
+// ------------------------------------------------------------------------------------------------
+struct P2pIface {
+    P2pPeers peers;
+    int rank, world, pay;
+    const double *rows_send;  // [2 nv^2]  (C | D) of this rank
+    double *rows_gath;        // [world][2 nv^2]
+    const double *rhs_send;   // [nv]
+    double *rhs_gath;         // [world][nv]
+    double *lu;               // [m][m] row-major, m = (world+1) nv
+    int *perm;                // [m] row swapped with k at step k
+    double *Zred;             // [world+1][nv]
+    unsigned long long left_mask, right_mask;
+};
+
+template <int NV>
+__device__ void iface_factor_block(const P2pIface &I, unsigned long long seq, unsigned *flags) {
+    constexpr int MMAX = (P2P_MAX_WORLD + 1) * NV;
+    __shared__ double K[MMAX][MMAX + 1];
+    __shared__ int s_piv;
+    const int m = (I.world + 1) * NV;
+    p2p_allgather_block(I.peers, I.rows_send, 2 * NV * NV, I.rows_gath, I.rank, I.world, I.pay, seq, flags);
+    for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) K[idx / m][idx % m] = 0.0;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < I.world * NV * NV; idx += blockDim.x) {
+        const int p = idx / (NV * NV), e = idx % (NV * NV), i = e / NV, c = e % NV;
+        K[p * NV + i][p * NV + c] = I.rows_gath[(size_t)p * 2 * NV * NV + e];
+        K[p * NV + i][(p + 1) * NV + c] = I.rows_gath[(size_t)p * 2 * NV * NV + NV * NV + e];
+    }
+    if (threadIdx.x == 0) {  // pinned components: unit rows
+        int row = I.world * NV;
+        for (int c = 0; c < NV; ++c)
+            if ((I.left_mask >> c) & 1ull) { if (row < m) K[row][c] = 1.0; ++row; }
+        for (int c = 0; c < NV; ++c)
+            if ((I.right_mask >> c) & 1ull) { if (row < m) K[row][I.world * NV + c] = 1.0; ++row; }
+        if (row != m) atomicOr(flags, RST_FLAG_ZERO_PIVOT);
+    }
+    __syncthreads();
+    for (int k = 0; k < m; ++k) {
+        if (threadIdx.x == 0) {
+            int p = k;
+            double best = fabs(K[k][k]);
+            for (int r = k + 1; r < m; ++r)
+                if (fabs(K[r][k]) > best) { best = fabs(K[r][k]); p = r; }
+            if (!(best > 0.0)) atomicOr(flags, RST_FLAG_ZERO_PIVOT);
+            s_piv = p;
+            I.perm[k] = p;
+        }
+        __syncthreads();
+        const int p = s_piv;
+        if (p != k)
+            for (int c = threadIdx.x; c < m; c += blockDim.x) { const double t = K[k][c]; K[k][c] = K[p][c]; K[p][c] = t; }
+        __syncthreads();
+        const double piv = K[k][k];
+        for (int r = k + 1 + threadIdx.x; r < m; r += blockDim.x) {
+            const double l = K[r][k] / piv;
+            K[r][k] = l;
+            for (int c = k + 1; c < m; ++c) K[r][c] = fma(-l, K[k][c], K[r][c]);
+        }
+        __syncthreads();
+    }
+    for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) I.lu[idx] = K[idx / m][idx % m];
+    __syncthreads();
+}
+
+template <int NV>
+__device__ void iface_solve_block(const P2pIface &I, unsigned long long seq, unsigned *flags) {
+    constexpr int MMAX = (P2P_MAX_WORLD + 1) * NV;
+    __shared__ double b[MMAX];
+    const int m = (I.world + 1) * NV;
+    p2p_allgather_block(I.peers, I.rhs_send, NV, I.rhs_gath, I.rank, I.world, I.pay, seq, flags);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) b[i] = i < I.world * NV ? I.rhs_gath[i] : 0.0;
+    __syncthreads();
+    if (threadIdx.x < 32) {  // one warp: row swaps, unit-lower then upper substitution with warp dot products
+        const int lane = threadIdx.x;
+        if (lane == 0)
+            for (int k = 0; k < m; ++k) {
+                const int p = I.perm[k];
+                if (p != k) { const double t = b[k]; b[k] = b[p]; b[p] = t; }
+            }
+        __syncwarp();
+        for (int i = 1; i < m; ++i) {
+            double s = 0.0;
+            for (int j = lane; j < i; j += 32) s = fma(I.lu[(size_t)i * m + j], b[j], s);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(RST_FULL_MASK, s, off);
+            if (lane == 0) b[i] -= s;
+            __syncwarp();
+        }
+        for (int i = m - 1; i >= 0; --i) {
+            double s = 0.0;
+            for (int j = i + 1 + lane; j < m; j += 32) s = fma(I.lu[(size_t)i * m + j], b[j], s);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(RST_FULL_MASK, s, off);
+            if (lane == 0) b[i] = (b[i] - s) / I.lu[(size_t)i * m + i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) I.Zred[i] = b[i];
+    __syncthreads();
+}
+
+}  // namespace rst

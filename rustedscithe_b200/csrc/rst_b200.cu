@@ -20,6 +20,7 @@
 #include "abd3.cuh"
 #include "tps.cuh"
 #include "btd.cuh"
+#include "p2p.cuh"
 #include "assemble.cuh"
 #include "newton.cuh"
 #include "generated_problems.cuh"  // from the -I generated directory (default: csrc/generated)
@@ -240,11 +241,30 @@ struct rst_b200_solver {
     int64_t *d_stream_src = nullptr;
     double *d_stream_out = nullptr;
     bool have_jac = false, factored = false;
+    // NVLink peer-memory all-gather (p2p.cuh)
+    double *mailbox = nullptr;
+    int p2p_pay = 0;
+    bool p2p_enabled = false;
+    P2pPeers peers{};
+    std::vector<void *> peer_mapped;
+    unsigned long long p2p_seq = 0;
+    P2pIface iface{};                  // interface system solved inside the single-CTA kernels (p2p.cuh)
+    double *iface_lu = nullptr;
+    int *iface_perm = nullptr;
     rst_b200_allgather_fn allgather = nullptr;
     void *allgather_ctx = nullptr;
     int64_t launches = 0;
     cudaEvent_t ev[2]{};
 };
+
+// nv == 2 path with mapped peers: the interface exchange + solve is fused into the single-CTA tail kernels
+static bool fused_p2p(const rst_b200_solver *s) { return s->use_tps && s->p2p_enabled && s->world > 1; }
+
+static P2pIface iface_args(const rst_b200_solver *s, bool fused) {
+    P2pIface I = s->iface;
+    if (!fused) I.world = 1;
+    return I;
+}
 
 static rst_b200_solver *g_bound = nullptr;  // handle behind the reference's handle-less AOT symbols
 
@@ -430,6 +450,12 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
             TRY(dev_alloc(s, &s->topA, (size_t)nv * nv));
             TRY(dev_alloc(s, &s->topB, (size_t)nv * nv));
             TRY(dev_alloc(s, &s->top_r, (size_t)nv));
+            s->p2p_pay = 2 * nv * nv > 8 ? 2 * nv * nv : 8;
+            const size_t mb = p2p_mailbox_doubles(world, s->p2p_pay);
+            TRY(dev_alloc(s, &s->mailbox, mb));
+            TRY(dev_alloc(s, &s->iface_lu, (size_t)((world + 1) * nv) * ((world + 1) * nv)));
+            TRY(dev_alloc(s, &s->iface_perm, (size_t)(world + 1) * nv));
+            CUDA_TRY(cudaMemsetAsync(s->mailbox, 0, mb * sizeof(double), s->stream));
         }
         s->use_tps = (nv == 2) && (std::getenv("RST_B200_NO_TPS") == nullptr);
         if (s->use_tps) {
@@ -539,6 +565,7 @@ extern "C" void rst_b200_destroy(rst_b200_solver *s) {
     if (g_bound == s) g_bound = nullptr;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    for (void *p : s->peer_mapped) cudaIpcCloseMemHandle(p);
     for (void *p : s->owned) cudaFree(p);
     if (s->h_scal) cudaFreeHost(s->h_scal);
     if (s->ev[0]) cudaEventDestroy(s->ev[0]);
@@ -735,7 +762,9 @@ extern "C" int rst_b200_factor_local(rst_b200_solver *s) {
             else tps_factor_kernel<2, TPS_S, false><<<blocks, 128, 0, s->stream>>>(lv, s->d_flags);
             s->launches++;
         }
-        tps_tail_factor_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, s->d_flags);
+        const bool fused = fused_p2p(s);
+        if (fused) s->p2p_seq++;
+        tps_tail_factor_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, iface_args(s, fused), s->p2p_seq, s->d_flags);
         s->launches++;
         CUDA_TRY(cudaGetLastError());
         return RST_B200_OK;
@@ -769,12 +798,63 @@ extern "C" int rst_b200_factor_reduced(rst_b200_solver *s) {
     return RST_B200_OK;
 }
 
+// all-gather of `count` doubles per rank: NVLink peer-memory kernel when the peers are mapped, host callback otherwise
+static int exchange(rst_b200_solver *s, const double *send, double *recv, int64_t count) {
+    if (s->p2p_enabled) {
+        s->p2p_seq++;
+        p2p_allgather_kernel<<<1, 256, 0, s->stream>>>(s->peers, send, (int)count, recv, s->rank, s->world, s->p2p_pay,
+                                                       s->p2p_seq, s->d_flags);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return RST_B200_OK;
+    }
+    if (!s->allgather) return fail(RST_B200_ERR_INVALID, "world > 1 needs rst_b200_p2p_open or rst_b200_set_allgather");
+    if (s->allgather(s->allgather_ctx, send, recv, count, s->stream) != 0)
+        return fail(RST_B200_ERR_CUDA, "all-gather callback failed");
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_p2p_get_handle(rst_b200_solver *s, void *handle_out, size_t handle_bytes) {
+    if (!s || !handle_out || handle_bytes < sizeof(cudaIpcMemHandle_t)) return fail(RST_B200_ERR_INVALID, "bad handle buffer");
+    if (!s->mailbox) return fail(RST_B200_ERR_INVALID, "world == 1 has no mailbox");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, s->mailbox));
+    std::memcpy(handle_out, &h, sizeof(h));
+    return RST_B200_OK;
+}
+
+// handles: [world][handle_stride bytes] in rank order (own entry ignored)
+extern "C" int rst_b200_p2p_open(rst_b200_solver *s, const void *handles, size_t handle_stride) {
+    if (!s || !handles || handle_stride < sizeof(cudaIpcMemHandle_t)) return fail(RST_B200_ERR_INVALID, "bad handle array");
+    if (s->world > P2P_MAX_WORLD || !s->mailbox) return fail(RST_B200_ERR_INVALID, "unsupported world size for peer access");
+    for (int p = 0; p < s->world; ++p) {
+        if (p == s->rank) { s->peers.mailbox[p] = s->mailbox; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char *)handles + (size_t)p * handle_stride, sizeof(h));
+        void *ptr = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_mapped.push_back(ptr);
+        s->peers.mailbox[p] = (double *)ptr;
+    }
+    s->p2p_enabled = true;
+    P2pIface &I = s->iface;
+    I.peers = s->peers;
+    I.rank = s->rank; I.world = s->world; I.pay = s->p2p_pay;
+    I.rows_send = s->iface_rows; I.rows_gath = s->gath_rows;
+    I.rhs_send = s->iface_rhs; I.rhs_gath = s->gath_rhs;
+    I.lu = s->iface_lu; I.perm = s->iface_perm; I.Zred = s->Zred;
+    I.left_mask = s->left_mask; I.right_mask = s->right_mask;
+    return RST_B200_OK;
+}
+
 extern "C" int rst_b200_factor(rst_b200_solver *s) {
     TRY(rst_b200_factor_local(s));
+    if (fused_p2p(s)) {  // exchange + interface factorisation already ran inside the tail kernel
+        s->factored = true;
+        return RST_B200_OK;
+    }
     if (s->world > 1) {
-        if (!s->allgather) return fail(RST_B200_ERR_INVALID, "world > 1 needs rst_b200_set_allgather");
-        if (s->allgather(s->allgather_ctx, s->iface_rows, s->gath_rows, 2 * (int64_t)s->nv * s->nv, s->stream) != 0)
-            return fail(RST_B200_ERR_CUDA, "all-gather callback failed");
+        TRY(exchange(s, s->iface_rows, s->gath_rows, 2 * (int64_t)s->nv * s->nv));
     }
     return rst_b200_factor_reduced(s);
 }
@@ -787,8 +867,8 @@ extern "C" int rst_b200_solve_local_forward(rst_b200_solver *s) {
             tps_forward_kernel<2, TPS_S><<<(unsigned)((lv.nslabs + 127) / 128), 128, 0, s->stream>>>(lv);
             s->launches++;
         }
-        if (s->world > 1) {  // single GPU: the tail's forward sweep is fused with the closure + backward sweep below
-            tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, 1, s->d_flags);
+        if (s->world > 1 && !fused_p2p(s)) {  // otherwise the tail's forward sweep is fused with closure + backward sweep
+            tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, iface_args(s, false), 0ull, 1, s->d_flags);
             s->launches++;
         }
         CUDA_TRY(cudaGetLastError());
@@ -804,8 +884,12 @@ extern "C" int rst_b200_solve_local_forward(rst_b200_solver *s) {
 
 extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
     if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
-    if (s->use_tps && s->world == 1) {
-        tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, 7, s->d_flags);
+    if (s->use_tps && (s->world == 1 || fused_p2p(s))) {
+        const bool fused = fused_p2p(s);
+        if (fused) s->p2p_seq++;
+        // forward sweeps -> closure (1 GPU) or NVLink interface exchange + solve (multi GPU) -> backward sweeps: ONE launch
+        tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, iface_args(s, fused), s->p2p_seq,
+                                                                   fused ? 13 : 7, s->d_flags);
         s->launches++;
         for (int i = (int)s->tps_big.size() - 1; i >= 0; --i) {
             const TpsLevel &lv = s->tps_big[i];
@@ -831,7 +915,7 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
         s->launches++;
     }
     if (s->use_tps) {
-        tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, 4, s->d_flags);
+        tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, iface_args(s, false), 0ull, 4, s->d_flags);
         s->launches++;
         for (int i = (int)s->tps_big.size() - 1; i >= 0; --i) {
             const TpsLevel &lv = s->tps_big[i];
@@ -851,10 +935,8 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
 
 extern "C" int rst_b200_solve(rst_b200_solver *s) {
     TRY(rst_b200_solve_local_forward(s));
-    if (s->world > 1) {
-        if (!s->allgather) return fail(RST_B200_ERR_INVALID, "world > 1 needs rst_b200_set_allgather");
-        if (s->allgather(s->allgather_ctx, s->iface_rhs, s->gath_rhs, (int64_t)s->nv, s->stream) != 0)
-            return fail(RST_B200_ERR_CUDA, "all-gather callback failed");
+    if (s->world > 1 && !fused_p2p(s)) {
+        TRY(exchange(s, s->iface_rhs, s->gath_rhs, (int64_t)s->nv));
     }
     return rst_b200_solve_reduced_backward(s);
 }
@@ -883,7 +965,10 @@ extern "C" int rst_b200_reduce_local(rst_b200_solver *s, int which_state) {
     a.partials = s->d_partials;
     a.n_rows = s->n;
     s->sv.reduce(a, s->red_blocks, s->stream);
-    newton_reduce_final_kernel<<<1, 256, 0, s->stream>>>(s->d_partials, s->red_blocks, s->d_scal, s->d_flags);
+    const bool fused_red = s->p2p_enabled && s->world > 1;
+    if (fused_red) s->p2p_seq++;
+    newton_reduce_final_kernel<<<1, 256, 0, s->stream>>>(s->d_partials, s->red_blocks, s->d_scal, s->d_flags, s->peers, s->rank,
+                                                         fused_red ? s->world : 1, s->p2p_pay, s->p2p_seq, s->d_gscal);
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return RST_B200_OK;
@@ -892,7 +977,7 @@ extern "C" int rst_b200_reduce_local(rst_b200_solver *s, int which_state) {
 extern "C" int rst_b200_reduce_finish(rst_b200_solver *s, rst_b200_scalars *out) {
     if (!s || !out) return fail(RST_B200_ERR_INVALID, "null argument");
     const double *src = s->d_scal;
-    if (s->world > 1) {
+    if (s->world > 1 && !s->p2p_enabled) {
         combine_scalars_kernel<<<1, 32, 0, s->stream>>>(s->d_gscal, s->world, s->d_scal);
         s->launches++;
     }
@@ -908,10 +993,8 @@ extern "C" int rst_b200_reduce_finish(rst_b200_solver *s, rst_b200_scalars *out)
 
 extern "C" int rst_b200_reduce(rst_b200_solver *s, int which_state, rst_b200_scalars *out) {
     TRY(rst_b200_reduce_local(s, which_state));
-    if (s->world > 1) {
-        if (!s->allgather) return fail(RST_B200_ERR_INVALID, "world > 1 needs rst_b200_set_allgather");
-        if (s->allgather(s->allgather_ctx, s->d_scal, s->d_gscal, 8, s->stream) != 0)
-            return fail(RST_B200_ERR_CUDA, "all-gather callback failed");
+    if (s->world > 1 && !s->p2p_enabled) {
+        TRY(exchange(s, s->d_scal, s->d_gscal, 8));
     }
     return rst_b200_reduce_finish(s, out);
 }
@@ -958,6 +1041,7 @@ static void set_solution_buffer(rst_b200_solver *s, double *buf) {
 // ---- damped Newton -------------------------------------------------------------------------------
 static int check_scalars(const rst_b200_scalars &sc) {
     if (sc.nan_flag != 0.0) return fail(RST_B200_ERR_NAN, "NaN in residual or Newton step");
+    if (((unsigned)sc.device_flags) & RST_FLAG_PEER_TIMEOUT) return fail(RST_B200_ERR_CUDA, "a peer rank never arrived at the interface exchange");
     if (((unsigned)sc.device_flags) & RST_FLAG_ZERO_PIVOT) return fail(RST_B200_ERR_ZERO_PIVOT, "zero pivot in block elimination");
     return RST_B200_OK;
 }

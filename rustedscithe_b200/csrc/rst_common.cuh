@@ -18,6 +18,7 @@
 #define RST_FLAG_ZERO_PIVOT 1u
 #define RST_FLAG_NAN_F 2u
 #define RST_FLAG_NAN_STEP 4u
+#define RST_FLAG_PEER_TIMEOUT 8u
 
 namespace rst {
 

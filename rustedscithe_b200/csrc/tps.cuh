@@ -15,6 +15,7 @@
 //   e: [ L (k, row>k) | per k: 1/pivot, U(k, c>k) | E (k,c) | F (k,c) ],  bits[(i-1)*nslabs + slab], e_rhs likewise.
 #pragma once
 #include "rst_common.cuh"
+#include "p2p.cuh"
 
 namespace rst {
 
@@ -324,7 +325,8 @@ __global__ void __launch_bounds__(128) tps_backward_kernel(TpsLevel L) {
 
 // ---- the tail: every remaining level inside one CTA -----------------------------------------------
 template <int NV, int S>
-__global__ void __launch_bounds__(256) tps_tail_factor_kernel(TpsTail T, unsigned *flags) {
+__global__ void __launch_bounds__(256) tps_tail_factor_kernel(TpsTail T, P2pIface I, unsigned long long seq,
+                                                              unsigned *flags) {
     for (int l = 0; l < T.nlevels; ++l) {
         const TpsLevel &L = T.lv[l];
         for (int64_t slab = threadIdx.x; slab < L.nslabs; slab += blockDim.x) {
@@ -335,6 +337,8 @@ __global__ void __launch_bounds__(256) tps_tail_factor_kernel(TpsTail T, unsigne
         }
         __syncthreads();
     }
+    // multi-GPU: gather every rank's interface row over NVLink and factor the interface system (same launch)
+    if (I.world > 1) iface_factor_block<NV>(I, seq, flags);
 }
 
 // boundary closure, serial in one thread (nv x nv, nv tiny): C Z0 + D Z1 = g with pinned components removed
@@ -378,9 +382,11 @@ __device__ void tps_top_solve(const double *C, const double *D, const double *g,
     for (int cc = 0; cc < NV; ++cc) Z[colmap[cc]] = K[cc][NV];
 }
 
-// phases: bit 0 forward sweeps, bit 1 boundary closure, bit 2 backward sweeps
+// phases: bit 0 forward sweeps, bit 1 boundary closure (single GPU), bit 3 interface exchange + solve (multi GPU),
+// bit 2 backward sweeps
 template <int NV, int S>
-__global__ void __launch_bounds__(256) tps_tail_solve_kernel(TpsTail T, int phases, unsigned *flags) {
+__global__ void __launch_bounds__(256) tps_tail_solve_kernel(TpsTail T, P2pIface I, unsigned long long seq, int phases,
+                                                             unsigned *flags) {
     if (phases & 1) {
         for (int l = 0; l < T.nlevels; ++l) {
             const TpsLevel &L = T.lv[l];
@@ -395,6 +401,7 @@ __global__ void __launch_bounds__(256) tps_tail_solve_kernel(TpsTail T, int phas
         }
         __syncthreads();
     }
+    if (phases & 8) iface_solve_block<NV>(I, seq, flags);
     if (phases & 4) {
         for (int l = T.nlevels - 1; l >= 0; --l) {
             const TpsLevel &L = T.lv[l];

@@ -272,6 +272,17 @@ class NRBVP:
     def launch_count(self):
         return int(self.L.rst_b200_launch_count(self.handle))
 
+    def p2p_handle(self) -> bytes:
+        """CUDA IPC handle (64 bytes) of this rank's NVLink mailbox."""
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.rst_b200_p2p_get_handle(self.handle, buf, 64))
+        return buf.raw
+
+    def p2p_open(self, handles):
+        """handles: list of every rank's p2p_handle() in rank order."""
+        blob = b"".join(handles)
+        self._ck(self.L.rst_b200_p2p_open(self.handle, blob, 64))
+
     def set_allgather(self, fn):
         """fn(d_send_ptr, d_recv_ptr, doubles_per_rank, stream_ptr) -> 0 on success."""
         def tramp(ctx, send, recv, count, stream):

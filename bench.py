@@ -356,8 +356,14 @@ def main():
                      "assemble_F": per_solve["linear_solves"] * phases["assemble_F"],
                      "solve": per_solve["linear_solves"] * phases["solve"]}
             dom = max(share, key=share.get)
+            # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel(s) from the committed `ncu --set full`
+            # captures (profiles/r01_b_summary.md), per launch at 1e6 intervals; None where no capture exists
+            ncu_traffic = {("flame12", "solve"): 2.426e9 + 3.575e9, ("flame12", "factor"): 1.153e9 + 5.620e9}
+            traffic = ncu_traffic.get((key, dom))
+            if traffic is not None:
+                traffic *= n_local / 1e6
             roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
-                        "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                        "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                         "share_of_step": share[dom] / ms_per_step,
                         "note": "solve = forward + backward sweeps over all condensation levels"}
 

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(128) abd_factor2_kernel(AbdLevel L, unsigned *
     const int64_t slab = ((int64_t)blockIdx.x * 4 + warp) * GPW + gw;
     const bool slab_ok = slab < L.nslabs;
     const bool lane_ok = r < NV;
+    const unsigned gmask = G == 32 ? RST_FULL_MASK : (((1u << (G & 31)) - 1u) << (gw * G));
     const int64_t g0 = slab * (int64_t)L.S;
     const int len = slab_ok ? (int)((L.n - g0) < (int64_t)L.S ? (L.n - g0) : (int64_t)L.S) : 0;
 
@@ -98,34 +99,27 @@ __global__ void __launch_bounds__(128) abd_factor2_kernel(AbdLevel L, unsigned *
         for (int k = 0; k < NV; ++k) {
             const bool cand0 = active && lane_ok && pv[0] < 0;
             const bool cand1 = active && lane_ok && pv[1] < 0;
+            // pivot search: 64-bit key = |value| bits with the low 5 mantissa bits replaced by (31 - row id); two REDUX.MAX
+            // (hi word, then lo word among the hi-word winners) give every lane the unique maximum key
             const long long k0 = cand0 ? ((__double_as_longlong(fabs(M[0][k])) & ~31LL) | (long long)(31 - 2 * r)) : -1LL;
             const long long k1 = cand1 ? ((__double_as_longlong(fabs(M[1][k])) & ~31LL) | (long long)(30 - 2 * r)) : -1LL;
-            long long key = k0 > k1 ? k0 : k1;
-#pragma unroll
-            for (int off = G / 2; off >= 1; off >>= 1) {
-                const long long o = __shfl_xor_sync(RST_FULL_MASK, key, off);
-                key = o > key ? o : key;
-            }
-            const int pid = 31 - (int)(key & 31LL);
+            const long long kk = k0 > k1 ? k0 : k1;
+            const bool cany = cand0 || cand1;
+            const unsigned hi = cany ? (unsigned)((unsigned long long)kk >> 32) + 1u : 0u;
+            const unsigned mhi = __reduce_max_sync(gmask, hi);
+            const unsigned lo = (cany && hi == mhi) ? (unsigned)kk : 0u;
+            const unsigned mlo = __reduce_max_sync(gmask, lo);
+            const int pid = 31 - (int)(mlo & 31u);
             const int pl = pid >> 1, ps = pid & 1;
             double2 *b2 = reinterpret_cast<double2 *>(&bc[warp][gw][k & 1][0]);
-            if (r == pl) {  // owner of the pivot row publishes it (STS.128 pairs)
-                if (ps == 0) {
+            if (r == pl) {  // owner of the pivot row publishes it (one STS.128 sequence, slot chosen by selects)
 #pragma unroll
-                    for (int c = (k & ~1); c < NV; c += 2) b2[c >> 1] = make_double2(M[0][c], M[0][c + 1]);
+                for (int c = (k & ~1); c < NV; c += 2)
+                    b2[c >> 1] = make_double2(ps ? M[1][c] : M[0][c], ps ? M[1][c + 1] : M[0][c + 1]);
 #pragma unroll
-                    for (int c = 0; c < NV; c += 2) {
-                        b2[(NV + c) >> 1] = make_double2(P[0][c], P[0][c + 1]);
-                        b2[(2 * NV + c) >> 1] = make_double2(Q[0][c], Q[0][c + 1]);
-                    }
-                } else {
-#pragma unroll
-                    for (int c = (k & ~1); c < NV; c += 2) b2[c >> 1] = make_double2(M[1][c], M[1][c + 1]);
-#pragma unroll
-                    for (int c = 0; c < NV; c += 2) {
-                        b2[(NV + c) >> 1] = make_double2(P[1][c], P[1][c + 1]);
-                        b2[(2 * NV + c) >> 1] = make_double2(Q[1][c], Q[1][c + 1]);
-                    }
+                for (int c = 0; c < NV; c += 2) {
+                    b2[(NV + c) >> 1] = make_double2(ps ? P[1][c] : P[0][c], ps ? P[1][c + 1] : P[0][c + 1]);
+                    b2[(2 * NV + c) >> 1] = make_double2(ps ? Q[1][c] : Q[0][c], ps ? Q[1][c + 1] : Q[0][c + 1]);
                 }
             }
             __syncwarp();
@@ -139,8 +133,9 @@ __global__ void __launch_bounds__(128) abd_factor2_kernel(AbdLevel L, unsigned *
             if (piv0) pv[0] = k;
             if (piv1) pv[1] = k;
             const bool u0 = cand0 && !piv0, u1 = cand1 && !piv1;
-            const double l0 = u0 ? M[0][k] / pivval : 0.0;
-            const double l1 = u1 ? M[1][k] / pivval : 0.0;
+            const double rc = __drcp_rn(pivval);
+            const double l0 = u0 ? M[0][k] * rc : 0.0;
+            const double l1 = u1 ? M[1][k] * rc : 0.0;
             if (u0) M[0][k] = l0;
             if (u1) M[1][k] = l1;
             if ((k & 1) == 0 && k + 1 < NV) {

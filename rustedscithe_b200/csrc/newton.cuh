@@ -156,6 +156,17 @@ __global__ void __launch_bounds__(256) newton_trial_kernel(const double *__restr
         Yt[idx] = Y[idx] - dY[idx] * lambda;
 }
 
+// same with lambda = 1.0 * fbound read from the device-resident reduction result (scal[2]): lets the first damping
+// trial be enqueued without a host round trip
+__global__ void __launch_bounds__(256) newton_trial_dev_kernel(const double *__restrict__ Y, const double *__restrict__ dY,
+                                                               double *__restrict__ Yt, const double *__restrict__ scal,
+                                                               int64_t total) {
+    const double lambda = 1.0 * scal[2];
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x)
+        Yt[idx] = Y[idx] - dY[idx] * lambda;
+}
+
 // ---- reduced ordering <-> full node-major state (numeric_discretization.rs:80-106, BVP_utils.rs:534-558) ----
 // reduced index k -> full position: the nl pinned slots of node 0 and the nr pinned slots of node N are deleted
 struct LayoutArgs {

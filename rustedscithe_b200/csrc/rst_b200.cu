@@ -241,6 +241,10 @@ struct rst_b200_solver {
     int64_t *d_stream_src = nullptr;
     double *d_stream_out = nullptr;
     bool have_jac = false, factored = false;
+    int fuse_reduce_state = -1;        // >= 0: the next solve fuses the damping reductions for that state (nv = 2 path)
+    int scal_slot = 0;                 // result slot (0/1) the next reduction writes to
+    int reduce_ready_state = -1;
+    int reduce_ready = 0;              // > 0: partials of that many blocks are waiting for the final reduction stage
     // NVLink peer-memory all-gather (p2p.cuh)
     double *mailbox = nullptr;
     int p2p_pay = 0;
@@ -544,10 +548,14 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
         }
         // reductions
         s->red_blocks = 148 * 4;
-        TRY(dev_alloc(s, &s->d_partials, (size_t)s->red_blocks * 4));
-        TRY(dev_alloc(s, &s->d_scal, (size_t)8));
+        {
+            size_t nb_part = (size_t)s->red_blocks;
+            if (s->use_tps && !s->tps_big.empty()) nb_part = std::max(nb_part, (size_t)((s->tps_big[0].nslabs + 127) / 128));
+            TRY(dev_alloc(s, &s->d_partials, nb_part * 4));
+        }
+        TRY(dev_alloc(s, &s->d_scal, (size_t)16));  // two result slots: undamped step / first damping trial
         TRY(dev_alloc(s, &s->d_gscal, (size_t)8 * world));
-        CUDA_TRY(cudaMallocHost((void **)&s->h_scal, 8 * sizeof(double)));
+        CUDA_TRY(cudaMallocHost((void **)&s->h_scal, 16 * sizeof(double)));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         return RST_B200_OK;
     };
@@ -893,9 +901,24 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
         s->launches++;
         for (int i = (int)s->tps_big.size() - 1; i >= 0; --i) {
             const TpsLevel &lv = s->tps_big[i];
-            tps_backward_kernel<2, TPS_S><<<(unsigned)((lv.nslabs + 127) / 128), 128, 0, s->stream>>>(lv);
+            const unsigned blocks = (unsigned)((lv.nslabs + 127) / 128);
+            if (i == 0 && s->fuse_reduce_state >= 0) {  // level 0: damping reductions ride along with the sweep
+                TpsReduce R{};
+                R.Y = s->fuse_reduce_state ? s->Yt : s->Y;
+                R.lo = s->d_lo; R.hi = s->d_hi; R.rtol = s->d_rtol;
+                R.left_mask = s->left_mask; R.right_mask = s->right_mask;
+                R.has_left = (s->rank == 0); R.has_right = (s->rank == s->world - 1);
+                R.n_own = (s->rank == s->world - 1) ? s->n + 1 : s->n;
+                R.partials = s->d_partials;
+                tps_backward_reduce_kernel<2, TPS_S><<<blocks, 128, 0, s->stream>>>(lv, R);
+                s->reduce_ready = (int)blocks;
+                s->reduce_ready_state = s->fuse_reduce_state;
+            } else {
+                tps_backward_kernel<2, TPS_S><<<blocks, 128, 0, s->stream>>>(lv);
+            }
             s->launches++;
         }
+        s->fuse_reduce_state = -1;
         CUDA_TRY(cudaGetLastError());
         return RST_B200_OK;
     }
@@ -919,9 +942,24 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
         s->launches++;
         for (int i = (int)s->tps_big.size() - 1; i >= 0; --i) {
             const TpsLevel &lv = s->tps_big[i];
-            tps_backward_kernel<2, TPS_S><<<(unsigned)((lv.nslabs + 127) / 128), 128, 0, s->stream>>>(lv);
+            const unsigned blocks = (unsigned)((lv.nslabs + 127) / 128);
+            if (i == 0 && s->fuse_reduce_state >= 0) {  // level 0: damping reductions ride along with the sweep
+                TpsReduce R{};
+                R.Y = s->fuse_reduce_state ? s->Yt : s->Y;
+                R.lo = s->d_lo; R.hi = s->d_hi; R.rtol = s->d_rtol;
+                R.left_mask = s->left_mask; R.right_mask = s->right_mask;
+                R.has_left = (s->rank == 0); R.has_right = (s->rank == s->world - 1);
+                R.n_own = (s->rank == s->world - 1) ? s->n + 1 : s->n;
+                R.partials = s->d_partials;
+                tps_backward_reduce_kernel<2, TPS_S><<<blocks, 128, 0, s->stream>>>(lv, R);
+                s->reduce_ready = (int)blocks;
+                s->reduce_ready_state = s->fuse_reduce_state;
+            } else {
+                tps_backward_kernel<2, TPS_S><<<blocks, 128, 0, s->stream>>>(lv);
+            }
             s->launches++;
         }
+        s->fuse_reduce_state = -1;
         CUDA_TRY(cudaGetLastError());
         return RST_B200_OK;
     }
@@ -964,10 +1002,17 @@ extern "C" int rst_b200_reduce_local(rst_b200_solver *s, int which_state) {
     a.has_left = (s->rank == 0); a.has_right = (s->rank == s->world - 1);
     a.partials = s->d_partials;
     a.n_rows = s->n;
-    s->sv.reduce(a, s->red_blocks, s->stream);
+    int nblocks = s->red_blocks;
+    if (s->reduce_ready > 0 && s->reduce_ready_state == (which_state ? 1 : 0)) {
+        nblocks = s->reduce_ready;  // produced by the fused level-0 backward sweep of the solve that just ran
+        s->launches--;
+    } else {
+        s->sv.reduce(a, s->red_blocks, s->stream);
+    }
+    s->reduce_ready = 0;
     const bool fused_red = s->p2p_enabled && s->world > 1;
     if (fused_red) s->p2p_seq++;
-    newton_reduce_final_kernel<<<1, 256, 0, s->stream>>>(s->d_partials, s->red_blocks, s->d_scal, s->d_flags, s->peers, s->rank,
+    newton_reduce_final_kernel<<<1, 256, 0, s->stream>>>(s->d_partials, nblocks, s->d_scal + 8 * s->scal_slot, s->d_flags, s->peers, s->rank,
                                                          fused_red ? s->world : 1, s->p2p_pay, s->p2p_seq, s->d_gscal);
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -1049,7 +1094,9 @@ static int check_scalars(const rst_b200_scalars &sc) {
 // NRBVP::step (:1782-1847) for state `which`: dY = J^{-1} F(y)
 static int newton_step(rst_b200_solver *s, int which, rst_b200_newton_stats *st) {
     TRY(rst_b200_eval_residual(s, which));
+    s->fuse_reduce_state = which;  // the reduction that follows this solve refers to state `which`
     TRY(rst_b200_solve(s));
+    s->fuse_reduce_state = -1;
     st->linear_solves++;
     return RST_B200_OK;
 }
@@ -1063,34 +1110,64 @@ static int recalc_jacobian(rst_b200_solver *s, rst_b200_newton_stats *st) {
 }
 
 // damped_step (:1862-2004).  Returns RST_B200_OK and the reference's status code in *status.
+static void unpack_scalars(const double *h, rst_b200_scalars *sc) {
+    sc->sumsq_step = h[0]; sc->tol_sum = h[1]; sc->fbound = h[2]; sc->nan_flag = h[3]; sc->device_flags = h[4];
+}
+
 static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b200_newton_stats *st, int *status) {
-    rst_b200_scalars sc{};
+    rst_b200_scalars sc{}, sc1{};
+    // trial steps go to dY1: the undamped step in dY is re-used by every damping trial (:1934, :1971)
+    struct Restore {
+        rst_b200_solver *s;
+        ~Restore() { set_solution_buffer(s, s->dY); s->scal_slot = 0; }
+    } restore{s};
+    // Device-only exchange (1 GPU, or NVLink mailboxes): the first damping trial uses lambda = fbound, which is already
+    // on the device, so undamped step + first trial are enqueued back to back and the host synchronises ONCE.
+    const bool speculative = (s->world == 1 || s->p2p_enabled) && o->max_damp_iter > 0;
+    s->scal_slot = 0;
     TRY(newton_step(s, 0, st));
-    TRY(rst_b200_reduce(s, 0, &sc));
+    if (speculative) {
+        TRY(rst_b200_reduce_local(s, 0));
+        set_solution_buffer(s, s->dY1);
+        const int64_t total = (s->n + 1) * (int64_t)s->nv;
+        newton_trial_dev_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY, s->Yt, s->d_scal, total);
+        s->launches++;
+        s->scal_slot = 1;
+        TRY(newton_step(s, 1, st));
+        TRY(rst_b200_reduce_local(s, 1));
+        s->scal_slot = 0;
+        CUDA_TRY(cudaMemcpyAsync(s->h_scal, s->d_scal, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        unpack_scalars(s->h_scal, &sc);
+        unpack_scalars(s->h_scal + 8, &sc1);
+    } else {
+        TRY(rst_b200_reduce(s, 0, &sc));
+    }
     TRY(check_scalars(sc));
     const double fbound = sc.fbound;
     st->last_fbound = fbound;
     if (std::isnan(fbound) || std::isinf(fbound)) return fail(RST_B200_ERR_NAN, "boundary step factor is not finite");
     double lambda = 1.0 * fbound;
-    if (fbound < 1e-10) { *status = -3; return RST_B200_OK; }
+    if (fbound < 1e-10) {
+        if (speculative) st->linear_solves--;  // the reference never takes that trial (:1898-1905)
+        *status = -3;
+        return RST_B200_OK;
+    }
     const double s0 = std::sqrt(sc.sumsq_step);
     st->last_s0 = s0;
     int k = 0;
     bool accepted = false;
     double s1 = 0.0, conv = 0.0;
-    // trial steps go to dY1: the undamped step in dY is re-used by every damping trial (:1934, :1971)
-    struct Restore {
-        rst_b200_solver *s;
-        ~Restore() { set_solution_buffer(s, s->dY); }
-    } restore{s};
     set_solution_buffer(s, s->dY1);
     while (k < o->max_damp_iter) {
-        TRY(rst_b200_make_trial(s, lambda));
-        TRY(newton_step(s, 1, st));
-        TRY(rst_b200_reduce(s, 1, &sc));
-        TRY(check_scalars(sc));
-        s1 = std::sqrt(sc.sumsq_step);
-        conv = sc.tol_sum > o->abs_tol ? sc.tol_sum : o->abs_tol;  // convergence_condition, BVP_utils_damped.rs:209-222
+        if (!(speculative && k == 0)) {
+            TRY(rst_b200_make_trial(s, lambda));
+            TRY(newton_step(s, 1, st));
+            TRY(rst_b200_reduce(s, 1, &sc1));
+        }
+        TRY(check_scalars(sc1));
+        s1 = std::sqrt(sc1.sumsq_step);
+        conv = sc1.tol_sum > o->abs_tol ? sc1.tol_sum : o->abs_tol;  // convergence_condition, BVP_utils_damped.rs:209-222
         st->last_lambda = lambda;
         if (s1 < 1.0 || s1 < s0) { accepted = true; break; }      // :1962
         lambda = lambda / std::pow(2.0, (double)k + o->damp_factor); // :1971

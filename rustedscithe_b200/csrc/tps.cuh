@@ -45,6 +45,41 @@ struct TpsTail {
     int do_top;
 };
 
+// damping reductions fused into the level-0 backward sweep (the sweep already holds every component of the step):
+// ||step||^2, sum |y| rtol and the Cantera bound factor (newton.cuh) without re-reading the step or the residual
+struct TpsReduce {
+    const double *Y;              // state the tolerance sum / bound guard refer to
+    const double *lo, *hi, *rtol; // per variable
+    unsigned long long left_mask, right_mask;
+    int has_left, has_right;
+    int64_t n_own;                // local nodes [0, n_own) belong to this rank
+    double *partials;             // [gridDim.x][4]
+};
+
+struct TpsRedAcc {
+    double ss, tol, fb, nanf;
+};
+
+template <int NV>
+__device__ __forceinline__ void tps_red_visit(const TpsReduce &R, TpsRedAcc &a, int64_t node, const double *step,
+                                              const double *y, const double *lo, const double *hi, const double *rt) {
+    if (node >= R.n_own) return;
+    unsigned long long pin = 0ull;
+    if (R.has_left && node == 0) pin |= R.left_mask;
+    if (R.has_right && node == R.n_own - 1) pin |= R.right_mask;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+        const double s = step[c], yy = y[c];
+        if (s != s) a.nanf = 2.0;
+        if ((pin >> c) & 1ull) continue;
+        a.ss = fma(s, s, a.ss);
+        a.tol = fma(fabs(yy), rt[c], a.tol);
+        const double nv_ = yy + s;
+        if (nv_ > hi[c]) a.fb = fmax(fmin(a.fb, (hi[c] - yy) / (nv_ - yy)), 0.0);
+        else if (nv_ < lo[c]) a.fb = fmin(a.fb, (yy - lo[c]) / (yy - nv_));
+    }
+}
+
 template <int NV>
 struct TpsCfg {
     static constexpr int R2 = 2 * NV;
@@ -231,8 +266,9 @@ __device__ __forceinline__ void tps_forward_slab(const TpsLevel &L, int64_t slab
     else tps_forward_slab_impl<NV, S, false>(L, slab);
 }
 
-template <int NV, int S, bool FULL>
-__device__ __forceinline__ void tps_backward_slab_impl(const TpsLevel &L, int64_t slab) {
+template <int NV, int S, bool FULL, bool REDUCE = false>
+__device__ __forceinline__ void tps_backward_slab_impl(const TpsLevel &L, int64_t slab, const TpsReduce *R = nullptr,
+                                                       TpsRedAcc *acc = nullptr) {
     using Cfg = TpsCfg<NV>;
     const int64_t g0 = slab * S;
     const int len = FULL ? S : (int)((L.n - g0) < (int64_t)S ? (L.n - g0) : (int64_t)S);
@@ -246,6 +282,22 @@ __device__ __forceinline__ void tps_backward_slab_impl(const TpsLevel &L, int64_
     if (slab == L.nslabs - 1) {
 #pragma unroll
         for (int c = 0; c < NV; ++c) L.Z[L.n * NV + c] = Yn[c];
+    }
+    double rlo[NV], rhi[NV], rrt[NV], ystate[S][NV];
+    if constexpr (REDUCE) {
+#pragma unroll
+        for (int c = 0; c < NV; ++c) { rlo[c] = R->lo[c]; rhi[c] = R->hi[c]; rrt[c] = R->rtol[c]; }
+#pragma unroll
+        for (int st = 0; st < S; ++st)
+#pragma unroll
+            for (int c = 0; c < NV; ++c) ystate[st][c] = (FULL || st < len) ? R->Y[(g0 + st) * NV + c] : 0.0;
+        tps_red_visit<NV>(*R, *acc, g0, Ys, ystate[0], rlo, rhi, rrt);
+        if (slab == L.nslabs - 1) {
+            double yl[NV];
+#pragma unroll
+            for (int c = 0; c < NV; ++c) yl[c] = R->Y[L.n * NV + c];
+            tps_red_visit<NV>(*R, *acc, L.n, Yn, yl, rlo, rhi, rrt);
+        }
     }
     // all loads of the slab first; the part of the right-hand side that only needs Y_s is folded in as data arrives,
     // so the dependent chain per step is just F * Y_next and the nv x nv triangular solve
@@ -296,6 +348,7 @@ __device__ __forceinline__ void tps_backward_slab_impl(const TpsLevel &L, int64_
             const int64_t g = g0 + st;
 #pragma unroll
             for (int c = 0; c < NV; ++c) L.Z[g * NV + c] = Yn[c];
+            if constexpr (REDUCE) tps_red_visit<NV>(*R, *acc, g, Yn, ystate[st], rlo, rhi, rrt);
         }
     }
 }
@@ -321,6 +374,36 @@ template <int NV, int S>
 __global__ void __launch_bounds__(128) tps_backward_kernel(TpsLevel L) {
     const int64_t slab = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slab < L.nslabs) tps_backward_slab<NV, S>(L, slab);
+}
+
+// level-0 backward sweep with the damping reductions fused in; one partial result per block
+template <int NV, int S>
+__global__ void __launch_bounds__(128) tps_backward_reduce_kernel(TpsLevel L, TpsReduce R) {
+    const int64_t slab = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TpsRedAcc acc{0.0, 0.0, 1.0, 0.0};
+    if (slab < L.nslabs) {
+        if ((slab + 1) * S <= L.n) tps_backward_slab_impl<NV, S, true, true>(L, slab, &R, &acc);
+        else tps_backward_slab_impl<NV, S, false, true>(L, slab, &R, &acc);
+    }
+    __shared__ double sh[4][4];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        acc.ss += __shfl_xor_sync(RST_FULL_MASK, acc.ss, off);
+        acc.tol += __shfl_xor_sync(RST_FULL_MASK, acc.tol, off);
+        acc.fb = fmin(acc.fb, __shfl_xor_sync(RST_FULL_MASK, acc.fb, off));
+        acc.nanf = fmax(acc.nanf, __shfl_xor_sync(RST_FULL_MASK, acc.nanf, off));
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sh[0][w] = acc.ss; sh[1][w] = acc.tol; sh[2][w] = acc.fb; sh[3][w] = acc.nanf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a0 = 0.0, a1 = 0.0, a2 = 1.0, a3 = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+            a0 += sh[0][i]; a1 += sh[1][i]; a2 = fmin(a2, sh[2][i]); a3 = fmax(a3, sh[3][i]);
+        }
+        double *p = R.partials + 4 * (int64_t)blockIdx.x;
+        p[0] = a0; p[1] = a1; p[2] = a2; p[3] = a3;
+    }
 }
 
 // ---- the tail: every remaining level inside one CTA -----------------------------------------------

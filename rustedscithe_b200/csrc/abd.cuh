@@ -36,6 +36,7 @@ struct AbdLevel {
     int64_t n;         // block rows at this level
     int64_t nslabs;    // ceil(n / S) = block rows of the next level
     int S;             // slab length (rows per slab)
+    int nv;            // block size (used by the run-time-nv kernels of big.cuh)
     const double *A;   // [n][nv][nv] row-major
     const double *B;   // [n][nv][nv] or nullptr (identity)
     double *A_next;    // [nslabs][nv][nv]

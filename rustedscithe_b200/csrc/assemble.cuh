@@ -117,6 +117,79 @@ __global__ void __launch_bounds__(128) assemble_kernel(AsmArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Wide blocks (nv > 16, config C5): a dense per-thread fy[nv*nv] cannot live in registers, so the emitter hands the
+// structural non-zeros of df/dy to a sink that stores  idsign*delta - hs*value  straight into the block.  The blocks
+// are initialised ONCE (rst_b200_create) with idsign*I; structural zeros are never written afterwards, so one assembly
+// pass writes NNZ + nv doubles per interval instead of nv*nv.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+struct BlockSink {
+    double *dst;
+    double hs, idsign;
+    __device__ __forceinline__ void put(int idx, double v) const {
+        st_cs(dst + idx, fma(-hs, v, (idx / NV) == (idx % NV) ? idsign : 0.0));
+    }
+};
+struct NullSink {
+    __device__ __forceinline__ void put(int, double) const {}
+};
+
+template <class P, bool WITH_J, bool TRAPEZOID>
+__global__ void __launch_bounds__(64) assemble_wide_kernel(AsmArgs a) {
+    constexpr int NV = P::NV;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.n) return;
+    double y0[NV], f0[NV];
+    load_node<NV>(a.Y + j * NV, y0);
+    double t, t1, h;
+    if (a.mesh) {
+        t = a.mesh[j];
+        t1 = a.mesh[j + 1];
+        h = t1 - t;
+    } else {
+        t = a.t0 + (double)(j + a.j_offset) * a.h;
+        t1 = a.t0 + (double)(j + a.j_offset + 1) * a.h;
+        h = a.h;
+    }
+    double *r = a.F + j * NV;
+    const double *yn = a.Y + (j + 1) * NV;
+    if constexpr (!TRAPEZOID) {
+        if constexpr (WITH_J) {
+            BlockSink<NV> sink{a.A + j * (int64_t)(NV * NV), h, -1.0};
+            P::eval_f_nz(t, y0, a.params, f0, sink);
+        } else {
+            P::eval_f(t, y0, a.params, f0);
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) r[i] = yn[i] - y0[i] - h * f0[i];
+    } else {
+        double y1[NV], f1[NV];
+        load_node<NV>(yn, y1);
+        const double tt = a.trap_time ? t1 : t;
+        if constexpr (WITH_J) {
+            BlockSink<NV> sa{a.A + j * (int64_t)(NV * NV), 0.5 * h, -1.0};
+            P::eval_f_nz(t, y0, a.params, f0, sa);
+            BlockSink<NV> sb{a.B + j * (int64_t)(NV * NV), 0.5 * h, 1.0};
+            P::eval_f_nz(tt, y1, a.params, f1, sb);
+        } else {
+            P::eval_f(t, y0, a.params, f0);
+            P::eval_f(tt, y1, a.params, f1);
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) r[i] = y1[i] - y0[i] - 0.5 * h * (f0[i] + f1[i]);
+    }
+}
+
+// blocks[j] = idsign * I  (run once at create for the wide path)
+__global__ void init_identity_blocks_kernel(double *blocks, int64_t n, int nv, double idsign) {
+    const int64_t total = n * nv * nv;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(idx % (nv * nv));
+        blocks[idx] = (e / nv) == (e % nv) ? idsign : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused F + J assembly with shared-memory staged block stores (nv >= 6).
 // In assemble_kernel every thread streams its own nv*nv block (1152 B at nv = 12) with 16-byte stores, i.e. a
 // warp store instruction touches 32 different 128-byte lines with half a sector each (measured 18 % of the HBM

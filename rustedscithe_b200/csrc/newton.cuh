@@ -110,6 +110,47 @@ __global__ void __launch_bounds__(256) newton_reduce_kernel(ReduceArgs a) {
     }
 }
 
+// run-time nv variant (wide blocks): same reductions, one element per thread iteration
+__global__ void __launch_bounds__(256) newton_reduce_generic_kernel(ReduceArgs a) {
+    double ss = 0.0, tol = 0.0, fb = 1.0, nanf = 0.0;
+    const int64_t total = a.n_nodes * a.nv;
+    const int64_t right0 = (a.n_nodes - 1) * a.nv;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t idx = tid; idx < total; idx += nthr) {
+        const double s = a.dY[idx], y = a.Y[idx];
+        if (s != s) nanf = 2.0;
+        const int v = (int)(idx % a.nv);
+        const bool pinned = (a.has_left && idx < a.nv && ((a.left_mask >> v) & 1ull)) ||
+                            (a.has_right && idx >= right0 && ((a.right_mask >> v) & 1ull));
+        if (pinned) continue;
+        ss = fma(s, s, ss);
+        tol = fma(fabs(y), a.rtol[v], tol);
+        const double nv_ = y + s;
+        if (nv_ > a.hi[v]) fb = fmax(fmin(fb, (a.hi[v] - y) / (nv_ - y)), 0.0);
+        else if (nv_ < a.lo[v]) fb = fmin(fb, (y - a.lo[v]) / (y - nv_));
+    }
+    if (a.F) {
+        const int64_t nf = a.n_rows * a.nv;
+        for (int64_t idx = tid; idx < nf; idx += nthr) {
+            const double f = a.F[idx];
+            if (f != f) nanf = fmax(nanf, 1.0);
+        }
+    }
+    __shared__ double sh[4][8];
+    ss = warp_sum(ss); tol = warp_sum(tol); fb = warp_min(fb); nanf = -warp_min(-nanf);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = ss; sh[1][w] = tol; sh[2][w] = fb; sh[3][w] = nanf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a0 = 0.0, a1 = 0.0, a2 = 1.0, a3 = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+            a0 += sh[0][i]; a1 += sh[1][i]; a2 = fmin(a2, sh[2][i]); a3 = fmax(a3, sh[3][i]);
+        }
+        double *p = a.partials + 4 * (int64_t)blockIdx.x;
+        p[0] = a0; p[1] = a1; p[2] = a2; p[3] = a3;
+    }
+}
+
 // deterministic second stage: out[0..3] = {sumsq, tolsum, fbound, nanflag}; out[4] = device error flags.
 // Multi-GPU with mapped peers: the 8-scalar all-gather over NVLink and the combination run in the same launch.
 __global__ void __launch_bounds__(256) newton_reduce_final_kernel(const double *partials, int nblocks, double *out,

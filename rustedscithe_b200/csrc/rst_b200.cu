@@ -21,6 +21,7 @@
 #include "tps.cuh"
 #include "btd.cuh"
 #include "p2p.cuh"
+#include "big.cuh"
 #include "assemble.cuh"
 #include "newton.cuh"
 #include "generated_problems.cuh"  // from the -I generated directory (default: csrc/generated)
@@ -55,6 +56,17 @@ static void launch_assemble(const AsmArgs &a, bool with_j, bool trap, cudaStream
     const int threads = 128;
     const unsigned blocks = (unsigned)((a.n + threads - 1) / threads);
     if (blocks == 0) return;
+    if constexpr (P::NV > 16) {  // wide blocks: sink-based emitter output, blocks pre-initialised with +-I at create
+        const unsigned wb = (unsigned)((a.n + 63) / 64);
+        if (!trap) {
+            if (with_j) assemble_wide_kernel<P, true, false><<<wb, 64, 0, st>>>(a);
+            else assemble_wide_kernel<P, false, false><<<wb, 64, 0, st>>>(a);
+        } else {
+            if (with_j) assemble_wide_kernel<P, true, true><<<wb, 64, 0, st>>>(a);
+            else assemble_wide_kernel<P, false, true><<<wb, 64, 0, st>>>(a);
+        }
+        return;
+    } else {
     // nv >= 6: blocks of A are staged through shared memory and streamed out coalesced (assemble.cuh)
     if constexpr (P::NV >= 6 && (P::NV % 2 == 0) && (32 * ((P::NV * P::NV) | 1) * 8 <= 48 * 1024)) {
         static const bool direct = std::getenv("RST_B200_ASSEMBLE_DIRECT") != nullptr;
@@ -71,6 +83,7 @@ static void launch_assemble(const AsmArgs &a, bool with_j, bool trap, cudaStream
     } else {
         if (with_j) assemble_kernel<P, true, true><<<blocks, threads, 0, st>>>(a);
         else assemble_kernel<P, false, true><<<blocks, threads, 0, st>>>(a);
+    }
     }
 }
 
@@ -97,7 +110,7 @@ struct SolverVT {
     void (*forward)(const AbdLevel &, cudaStream_t);
     void (*backward)(const AbdLevel &, cudaStream_t);
     void (*top)(const double *C, const double *D, const double *g, double *Z, unsigned long long lm,
-                unsigned long long rm, unsigned *flags, cudaStream_t);
+                unsigned long long rm, unsigned *flags, int nv, cudaStream_t);
     void (*residual)(const double *A, const double *B, const double *X, const double *rhs, double *out, int64_t n,
                      cudaStream_t);
     void (*reduce)(const ReduceArgs &, int blocks, cudaStream_t);
@@ -159,7 +172,7 @@ struct SolverImpl {
         abd_backward_kernel<NV><<<grid_for(L.nslabs, NV), 128, 0, st>>>(L);
     }
     static void top(const double *C, const double *D, const double *g, double *Z, unsigned long long lm,
-                    unsigned long long rm, unsigned *flags, cudaStream_t st) {
+                    unsigned long long rm, unsigned *flags, int, cudaStream_t st) {
         abd_top_solve_kernel<NV><<<1, 32, 0, st>>>(C, D, g, Z, lm, rm, flags);
     }
     static void residual(const double *A, const double *B, const double *X, const double *rhs, double *out, int64_t n,
@@ -177,7 +190,41 @@ struct SolverImpl {
     static SolverVT vt() { return SolverVT{NV, &factor, &forward, &backward, &top, &residual, &reduce, &top_general}; }
 };
 
-static bool solver_vt_for(int nv, SolverVT *out) {
+// wide blocks (16 < nv <= 64, or any nv >= 3 with RST_B200_FORCE_BIG): run-time-nv block-per-slab kernels (big.cuh)
+struct BigImpl {
+    static void factor(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
+        const size_t smem = big_factor_smem_bytes(L.nv);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(big_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_factor_smem_bytes(BIG_MAX_NV));
+            cudaFuncSetAttribute(big_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_factor_smem_bytes(BIG_MAX_NV));
+            attr_set = true;
+        }
+        if (ident_b) big_factor_kernel<true><<<(unsigned)L.nslabs, BIG_THREADS, smem, st>>>(L, L.nv, flags);
+        else big_factor_kernel<false><<<(unsigned)L.nslabs, BIG_THREADS, smem, st>>>(L, L.nv, flags);
+    }
+    static void forward(const AbdLevel &L, cudaStream_t st) { big_forward_kernel<<<(unsigned)L.nslabs, 128, 0, st>>>(L, L.nv); }
+    static void backward(const AbdLevel &L, cudaStream_t st) { big_backward_kernel<<<(unsigned)L.nslabs, 64, 0, st>>>(L, L.nv); }
+    static void top(const double *C, const double *D, const double *g, double *Z, unsigned long long lm,
+                    unsigned long long rm, unsigned *flags, int nv, cudaStream_t st) {
+        big_top_solve_kernel<<<1, 32, 0, st>>>(C, D, g, Z, nv, lm, rm, flags);
+    }
+    static void reduce(const ReduceArgs &a, int blocks, cudaStream_t st) {
+        newton_reduce_generic_kernel<<<blocks, 256, 0, st>>>(a);
+    }
+    static SolverVT vt(int nv) { return SolverVT{nv, &factor, &forward, &backward, &top, nullptr, &reduce, nullptr}; }
+};
+
+static bool use_big_path(int nv) {
+    return nv > 16 || (nv >= 3 && std::getenv("RST_B200_FORCE_BIG") != nullptr);  // env: test hook, read per create
+}
+
+static bool solver_vt_for(int nv, SolverVT *out, bool allow_big = true) {
+    if (allow_big && use_big_path(nv)) {
+        if (nv > BIG_MAX_NV) return false;
+        *out = BigImpl::vt(nv);
+        return true;
+    }
     switch (nv) {
 #define RST_NV(n) case n: *out = SolverImpl<n>::vt(); return true;
 #include "generated_nv_list.inc"  // block sizes of the compiled-in problems + the BlockTridiagonal drop-in sizes
@@ -301,6 +348,7 @@ static int build_level(H *s, LevelBuf *lv, int64_t n, int S, const double *A, co
     AbdLevel &k = lv->k;
     k.n = n;
     k.S = S;
+    k.nv = nv;
     k.nslabs = (n + S - 1) / S;
     k.A = A;
     k.B = B;
@@ -421,6 +469,10 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
         TRY(dev_alloc(s, &s->F, (size_t)n * nv));
         TRY(dev_alloc(s, &s->A, (size_t)n * nv * nv));
         if (s->scheme == RST_B200_SCHEME_TRAPEZOID) TRY(dev_alloc(s, &s->B, (size_t)n * nv * nv));
+        if (nv > 16) {  // wide path: assembly writes structural non-zeros only (assemble.cuh)
+            init_identity_blocks_kernel<<<148 * 8, 256, 0, s->stream>>>(s->A, n, nv, -1.0);
+            if (s->B) init_identity_blocks_kernel<<<148 * 8, 256, 0, s->stream>>>(s->B, n, nv, 1.0);
+        }
         TRY(dev_alloc(s, &s->d_tmp, nodes + nv));
         TRY(dev_alloc(s, &s->d_params, (size_t)(s->np > 0 ? s->np : 1)));
         TRY(dev_alloc(s, &s->d_lo, (size_t)nv));
@@ -931,7 +983,7 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
     } else {
         C = s->iface_rows; D = s->iface_rows + s->nv * s->nv; g = s->iface_rhs;
     }
-    s->sv.top(C, D, g, s->Ztop, s->left_mask, s->right_mask, s->d_flags, s->stream);
+    s->sv.top(C, D, g, s->Ztop, s->left_mask, s->right_mask, s->d_flags, s->nv, s->stream);
     s->launches++;
     if (s->have_red) {
         s->sv.backward(s->red.k, s->stream);
@@ -1439,7 +1491,7 @@ extern "C" int rst_b200_btd_create(int64_t n_blocks, int block_size, int device,
     rst_b200_btd *s = new rst_b200_btd();
     s->bs = block_size;
     s->nv = 2 * block_size;
-    if (!solver_vt_for(s->nv, &s->sv)) {
+    if (!solver_vt_for(s->nv, &s->sv, false)) {
         delete s;
         return fail(RST_B200_ERR_UNSUPPORTED, "block size not compiled in (supported: 1, 2, 3, 4, 6, 8)");
     }

@@ -25,6 +25,7 @@ from dataclasses import dataclass
 import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
+WIDE_NV = 16   # above this block size the Jacobian is emitted through a sink (eval_f_nz) instead of a dense fy[]
 ALLOWED_FUNCS = {"exp", "log", "sin", "cos", "tan", "cot", "asin", "acos", "atan", "acot"}
 
 
@@ -146,12 +147,23 @@ def emit_problem(spec) -> EmittedProblem:
     src.append("        (void)t; (void)y; (void)p;")
     src += f_lines
     src.append("    }")
-    src.append("    // f and the zero-pruned df/dy (row-major NV*NV, structural zeros written as 0.0)")
-    src.append("    __device__ __forceinline__ static void eval_f_fy(double t, const double *y, const double *p, double *f, double *fy) {")
-    src.append("        (void)t; (void)y; (void)p;")
-    src += zero_lines
-    src += fj_lines
-    src.append("    }")
+    if nv <= WIDE_NV:
+        src.append("    // f and the zero-pruned df/dy (row-major NV*NV, structural zeros written as 0.0)")
+        src.append("    __device__ __forceinline__ static void eval_f_fy(double t, const double *y, const double *p, double *f, double *fy) {")
+        src.append("        (void)t; (void)y; (void)p;")
+        src += zero_lines
+        src += fj_lines
+        src.append("    }")
+    else:
+        # wide blocks: a dense per-thread fy[NV*NV] would live in local memory; the structural non-zeros are handed to a
+        # sink (the assembly kernel stores them straight into the pre-initialised block, csrc/assemble.cuh)
+        src.append("    // f and the structural non-zeros of df/dy: sink.put(row * NV + col, value), each entry exactly once")
+        src.append("    template <class Sink>")
+        src.append("    __device__ __forceinline__ static void eval_f_nz(double t, const double *y, const double *p, double *f, Sink &sink) {")
+        src.append("        (void)t; (void)y; (void)p;")
+        src += [ln.replace("        fy[", "        sink.put(").replace("] = ", ", ", 1).replace(";", ");")
+                if ln.startswith("        fy[") else ln for ln in fj_lines]
+        src.append("    }")
     src.append("};")
     text = "\n".join(src) + "\n"
     return EmittedProblem(spec.key, nv, len(psyms), pattern, text,

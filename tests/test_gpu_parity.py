@@ -37,7 +37,8 @@ def _rel(a, b, floor=1.0):
     return np.max(np.abs(a - b) / np.maximum(floor, np.abs(b)))
 
 
-CASES = [("linear2", 1000), ("damp1", 128), ("damp1p", 77), ("combustion6", 300), ("flame12", 257), ("coupled8", 100)]
+CASES = [("linear2", 1000), ("damp1", 128), ("damp1p", 77), ("combustion6", 300), ("flame12", 257), ("coupled8", 100),
+         ("coupled64", 40)]
 
 
 @pytest.mark.parametrize("key,n_steps", CASES)
@@ -96,7 +97,7 @@ def test_nonuniform_mesh_and_parameters():
 SOLVE_CASES = [
     ("linear2", 1000, 0), ("linear2", 37, 4), ("linear2", 2, 0), ("linear2", 3, 2), ("damp1", 128, 8),
     ("combustion6", 1000, 0), ("combustion6", 333, 5), ("flame12", 500, 0), ("flame12", 2000, 32),
-    ("flame12", 65, 64), ("coupled8", 200, 3),
+    ("flame12", 65, 64), ("coupled8", 200, 3), ("coupled64", 60, 0), ("coupled64", 37, 5),
 ]
 
 
@@ -130,6 +131,27 @@ def test_linear_solve_matches_faithful_banded_lu(key, n_steps, slab, scheme):
     g.close()
 
 
+@pytest.mark.parametrize("key,n_steps,slab", [("flame12", 500, 0), ("coupled8", 200, 3), ("combustion6", 333, 5)])
+@pytest.mark.parametrize("scheme", ["forward", "trapezoid"])
+def test_block_per_slab_kernels_on_narrow_blocks(key, n_steps, slab, scheme, monkeypatch):
+    """The run-time-nv block-per-slab kernels (csrc/big.cuh, used for 16 < nv <= 64) forced onto narrow problems: same
+    factor layout, same answers as the banded LU."""
+    monkeypatch.setenv("RST_B200_FORCE_BIG", "1")
+    rng = np.random.default_rng(29)
+    spec = problems.get(key)
+    o = _oracle(key, n_steps, scheme)
+    g = _gpu(key, n_steps, scheme, slab=slab)
+    y = spec.guess(n_steps) * (1.0 + 0.01 * rng.standard_normal(o.n))
+    vals, rhs = o.jacobian_values(y), o.residual(y)
+    dy_ref = o.solve_banded(vals, rhs)
+    g.set_state(y)
+    g.eval_jacobian()
+    g.factor()
+    dy = g.solve_in_place(rhs)
+    assert np.linalg.norm(dy - dy_ref) / np.linalg.norm(dy_ref) < TOL_DY
+    g.close()
+
+
 def test_solver_error_behaviour():
     from rustedscithe_b200 import lib as rlib
     g = _gpu("linear2", 64)
@@ -159,7 +181,7 @@ def test_singular_system_reports_zero_pivot():
 
 
 NEWTON_CASES = [("linear2", 80), ("linear2", 1000), ("damp1", 64), ("combustion6", 1000), ("flame12", 400),
-                ("coupled8", 150), ("combustion6", 50), ("flame12", 33)]
+                ("coupled8", 150), ("combustion6", 50), ("flame12", 33), ("coupled64", 48)]
 
 
 @pytest.mark.parametrize("key,n_steps", NEWTON_CASES)

@@ -115,26 +115,29 @@ static void flame12_rhs(double t, const double *y, const double *p, double *f) {
 static void flame12_jac(double t, const double *y, const double *p, double *fy) { (void)t; (void)p; flame_jac_n(5, y, fy); }
 
 /* ---------------- coupled template (coupled64 = 31 species): dense C-coupling ----------------
- * rate_k = A exp(-E_k/(R T)) (ro_m/M) sum_m a_km C_m,  a_km = 1/(1+|k-m|),  E_k = E (1 + 0.01 k)
+ * rate_k = A exp(-E_k/(R T)) (ro_m/M) (e0 C_0 + eps sum_m a_km C_m),  a_km = 1/(1+|k-m|),  E_k = E (1 + 0.01 k)
+ * coupled8: (eps, e0) = (1, 0);  coupled64: (0.01, 1) -- weak dense coupling on top of the flame rate law so that the
+ * reference's damped loop converges from the flat guess
  * Teta' = q/lambda ; q' = Pe_q q - Q qm sum_k w_k rate_k ; C_k' = J_k/(ro D) ;
  * J_k' = Pe_D J_k + s_k rate_k ro_m qs,  s_0 = +1, s_k = -w_k,  w_k = 1/nsp */
-static void coupled_rates(int nsp, const double *y, double *rate, double *ex) {
+static void coupled_rates(int nsp, double eps, double e0, const double *y, double *rate, double *ex) {
     const double ro_m = M0 * P_PRESS / (R_G * TM);
     const double T = y[0] * T_SCALE + DT;
     for (int k = 0; k < nsp; ++k) {
         const double Ek = E_ACT * (1.0 + 0.01 * (double)k);
         double s = 0.0;
-        for (int m = 0; m < nsp; ++m) s += y[2 + 2 * m] / (1.0 + (double)(k > m ? k - m : m - k));
+        for (int m = 0; m < nsp; ++m) s += eps * y[2 + 2 * m] / (1.0 + (double)(k > m ? k - m : m - k));
+        s += e0 * y[2];
         ex[k] = A_PRE * exp(-Ek / (R_G * T)) * (ro_m / M_REAG);
         rate[k] = ex[k] * s;
     }
 }
-static void coupled_rhs_n(int nsp, const double *y, double *f) {
+static void coupled_rhs_n(int nsp, double eps, double e0, const double *y, double *f) {
     const double ro_m = M0 * P_PRESS / (R_G * TM);
     const double qm = pow(L_LEN, 2.0) / T_SCALE;
     const double qs = pow(L_LEN, 2.0);
     double rate[64], ex[64];
-    coupled_rates(nsp, y, rate, ex);
+    coupled_rates(nsp, eps, e0, y, rate, ex);
     const double w = 1.0 / (double)nsp;
     double heat = 0.0;
     for (int k = 0; k < nsp; ++k) heat += w * rate[k];
@@ -147,14 +150,14 @@ static void coupled_rhs_n(int nsp, const double *y, double *f) {
         f[3 + 2 * k] = jk * PE_D + s * rate[k] * ro_m * qs;
     }
 }
-static void coupled_jac_n(int nsp, const double *y, double *fy) {
+static void coupled_jac_n(int nsp, double eps, double e0, const double *y, double *fy) {
     const int nv = 2 + 2 * nsp;
     const double ro_m = M0 * P_PRESS / (R_G * TM);
     const double qm = pow(L_LEN, 2.0) / T_SCALE;
     const double qs = pow(L_LEN, 2.0);
     const double T = y[0] * T_SCALE + DT;
     double rate[64], ex[64];
-    coupled_rates(nsp, y, rate, ex);
+    coupled_rates(nsp, eps, e0, y, rate, ex);
     const double w = 1.0 / (double)nsp;
     memset(fy, 0, sizeof(double) * (size_t)nv * nv);
     fy[0 * nv + 1] = 1.0 / LAMBDA;
@@ -169,16 +172,16 @@ static void coupled_jac_n(int nsp, const double *y, double *fy) {
         fy[rj * nv + 0] = s * ro_m * qs * drdteta;
         fy[1 * nv + 0] += -Q_HEAT * qm * w * drdteta;
         for (int m = 0; m < nsp; ++m) {
-            const double a = 1.0 / (1.0 + (double)(k > m ? k - m : m - k));
+            const double a = eps / (1.0 + (double)(k > m ? k - m : m - k)) + (m == 0 ? e0 : 0.0);
             fy[rj * nv + 2 + 2 * m] = s * ro_m * qs * ex[k] * a;
             fy[1 * nv + 2 + 2 * m] += -Q_HEAT * qm * w * ex[k] * a;
         }
     }
 }
-static void coupled64_rhs(double t, const double *y, const double *p, double *f) { (void)t; (void)p; coupled_rhs_n(31, y, f); }
-static void coupled64_jac(double t, const double *y, const double *p, double *fy) { (void)t; (void)p; coupled_jac_n(31, y, fy); }
-static void coupled8_rhs(double t, const double *y, const double *p, double *f) { (void)t; (void)p; coupled_rhs_n(3, y, f); }
-static void coupled8_jac(double t, const double *y, const double *p, double *fy) { (void)t; (void)p; coupled_jac_n(3, y, fy); }
+static void coupled64_rhs(double t, const double *y, const double *p, double *f) { (void)t; (void)p; coupled_rhs_n(31, 0.01, 1.0, y, f); }
+static void coupled64_jac(double t, const double *y, const double *p, double *fy) { (void)t; (void)p; coupled_jac_n(31, 0.01, 1.0, y, fy); }
+static void coupled8_rhs(double t, const double *y, const double *p, double *f) { (void)t; (void)p; coupled_rhs_n(3, 1.0, 0.0, y, f); }
+static void coupled8_jac(double t, const double *y, const double *p, double *fy) { (void)t; (void)p; coupled_jac_n(3, 1.0, 0.0, y, fy); }
 
 /* ---------------- parameterised test problem: z' = y - z, y' = p0 * z^3 + p1 * t ---------------- */
 static void damp1p_rhs(double t, const double *y, const double *p, double *f) {

@@ -179,7 +179,7 @@ FLAME12 = _flame_spec("flame12", 5)
 
 
 # ---- coupled template (C5): every rate depends on all C_k --------------------------------------------
-def _coupled_rhs(nsp):
+def _coupled_rhs(nsp, eps=1.0, e0=0.0):
     def build():
         import sympy as sp
         c = {k: sp.Float(v, 17) for k, v in _flame_consts().items()}
@@ -190,7 +190,9 @@ def _coupled_rhs(nsp):
         rates = []
         for k in range(nsp):
             ek = sp.Float(_flame_consts()["e"] * (1.0 + 0.01 * k), 17)
-            ssum = sum(s[2 + 2 * m] / sp.Float(1.0 + abs(k - m), 17) for m in range(nsp))
+            ssum = sum(sp.Float(eps, 17) * s[2 + 2 * m] / sp.Float(1.0 + abs(k - m), 17) for m in range(nsp))
+            if e0:
+                ssum = ssum + sp.Float(e0, 17) * s[2]
             rates.append(c["a"] * sp.exp(-ek / (c["r_g"] * T)) * (c["ro_m"] / c["m_reag"]) * ssum)
         heat = sum(w * r for r in rates)
         eqs = [q / c["lam"], q * c["pe_q"] - c["q_heat"] * c["qm"] * heat]
@@ -203,14 +205,20 @@ def _coupled_rhs(nsp):
     return build
 
 
-def _coupled_spec(key, nsp):
+def _coupled_spec(key, nsp, eps=1.0, e0=0.0, relax_bounds=False):
     spec = _flame_spec(key, nsp)
-    spec.rhs = _coupled_rhs(nsp)
+    spec.rhs = _coupled_rhs(nsp, eps, e0)
+    if not relax_bounds:
+        return spec
+    # with many weakly produced species the first Newton iterates undershoot C_k = 0 slightly; the flame bounds (0, 1.5)
+    # would stop the reference's damped loop at the bound (fbound < 1e-10), so the synthetic wide case relaxes them
+    for k in range(nsp):
+        spec.bounds[f"C{k}"] = (-1.0, 2.0)
     return spec
 
 
 COUPLED8 = _coupled_spec("coupled8", 3)
-COUPLED64 = _coupled_spec("coupled64", 31)
+COUPLED64 = _coupled_spec("coupled64", 31, eps=0.01, e0=1.0, relax_bounds=True)
 
 CATALOGUE = {p.key: p for p in [LINEAR2, DAMP1, DAMP1P, COMBUSTION6, FLAME12, COUPLED8, COUPLED64]}
 

@@ -309,7 +309,8 @@ def test_config_c3_million_points_newton_converges_and_residual_vanishes():
 
 
 # ---- multi-rank path, emulated in one process through the phase-split ABI --------------------------------
-@pytest.mark.parametrize("key,n_steps,world", [("linear2", 101, 2), ("flame12", 300, 3), ("combustion6", 64, 4)])
+@pytest.mark.parametrize("key,n_steps,world", [("linear2", 101, 2), ("flame12", 300, 3), ("combustion6", 64, 4),
+                                                ("coupled64", 40, 2)])
 def test_emulated_mesh_slab_ranks_match_single_rank(key, n_steps, world):
     import ctypes as C
     spec = problems.get(key)

@@ -192,7 +192,26 @@ struct SolverImpl {
 
 // wide blocks (16 < nv <= 64, or any nv >= 3 with RST_B200_FORCE_BIG): run-time-nv block-per-slab kernels (big.cuh)
 struct BigImpl {
+    template <int NVP>
+    static void factor_tiled(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
+        using C = BigrCfg<NVP>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(bigr_factor_kernel<NVP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
+            cudaFuncSetAttribute(bigr_factor_kernel<NVP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
+            attr_set = true;
+        }
+        if (ident_b) bigr_factor_kernel<NVP, true><<<(unsigned)L.nslabs, C::THREADS, C::smem_bytes, st>>>(L, L.nv, flags);
+        else bigr_factor_kernel<NVP, false><<<(unsigned)L.nslabs, C::THREADS, C::smem_bytes, st>>>(L, L.nv, flags);
+    }
     static void factor(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
+        // default: register-tiled panel (FP64-pipe bound); RST_B200_BIG_V1 selects the first shared-memory-panel kernel
+        static const bool v1 = std::getenv("RST_B200_BIG_V1") != nullptr;
+        if (!v1) {
+            if (L.nv <= 32) factor_tiled<32>(L, ident_b, flags, st);
+            else factor_tiled<64>(L, ident_b, flags, st);
+            return;
+        }
         const size_t smem = big_factor_smem_bytes(L.nv);
         static bool attr_set = false;
         if (!attr_set) {
@@ -203,8 +222,36 @@ struct BigImpl {
         if (ident_b) big_factor_kernel<true><<<(unsigned)L.nslabs, BIG_THREADS, smem, st>>>(L, L.nv, flags);
         else big_factor_kernel<false><<<(unsigned)L.nslabs, BIG_THREADS, smem, st>>>(L, L.nv, flags);
     }
-    static void forward(const AbdLevel &L, cudaStream_t st) { big_forward_kernel<<<(unsigned)L.nslabs, 128, 0, st>>>(L, L.nv); }
-    static void backward(const AbdLevel &L, cudaStream_t st) { big_backward_kernel<<<(unsigned)L.nslabs, 64, 0, st>>>(L, L.nv); }
+    // sweeps: generation 2 streams the factors through a shared-memory ring with bulk async copies (needs 16-byte
+    // aligned stages, i.e. even nv); RST_B200_BIG_V1 or odd nv select the first kernels
+    static bool pipelined(int nv) {
+        static const bool v1 = std::getenv("RST_B200_BIG_V1") != nullptr;
+        return !v1 && (nv % 2 == 0);
+    }
+    static void forward(const AbdLevel &L, cudaStream_t st) {
+        if (!pipelined(L.nv)) {
+            big_forward_kernel<<<(unsigned)L.nslabs, 128, 0, st>>>(L, L.nv);
+            return;
+        }
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(bigp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bigp_forward_smem(BIG_MAX_NV));
+            attr_set = true;
+        }
+        bigp_forward_kernel<<<(unsigned)L.nslabs, BIGP_THREADS, bigp_forward_smem(L.nv), st>>>(L, L.nv);
+    }
+    static void backward(const AbdLevel &L, cudaStream_t st) {
+        if (!pipelined(L.nv)) {
+            big_backward_kernel<<<(unsigned)L.nslabs, 64, 0, st>>>(L, L.nv);
+            return;
+        }
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(bigp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bigp_backward_smem(BIG_MAX_NV));
+            attr_set = true;
+        }
+        bigp_backward_kernel<<<(unsigned)L.nslabs, BIGP_THREADS, bigp_backward_smem(L.nv), st>>>(L, L.nv);
+    }
     static void top(const double *C, const double *D, const double *g, double *Z, unsigned long long lm,
                     unsigned long long rm, unsigned *flags, int nv, cudaStream_t st) {
         big_top_solve_kernel<<<1, 32, 0, st>>>(C, D, g, Z, nv, lm, rm, flags);

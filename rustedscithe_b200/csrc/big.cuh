@@ -269,6 +269,10 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
 #pragma unroll
                 for (int i = 0; i < RT; ++i) key = max(key, ((__double2hiint(a[i][jk]) & 0x7fffff80) | keytag) + (7 - i));
                 key = __shfl_sync(RST_FULL_MASK, key, kk);
+                // column k of this warp's rows, broadcast to every lane (becomes the multipliers after the barrier)
+                double l[RT];
+#pragma unroll
+                for (int i = 0; i < RT; ++i) l[i] = __shfl_sync(RST_FULL_MASK, a[i][jk], kk);
                 const int bi = 7 - (key & 7);
                 double *myslot = slot + (par * NW + ty) * SLOTW + tx;
                 double cand = 0.0;
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
     case I:                                                                                         \
         if (I < RT) {                                                                               \
             _Pragma("unroll") for (int j = jk; j < CT; ++j) myslot[32 * j] = a[I < RT ? I : 0][j];  \
-            cand = a[I < RT ? I : 0][jk];                                                           \
+            cand = l[I < RT ? I : 0];                                                               \
         }                                                                                           \
         break;
                     BIGR_PUBLISH(0) BIGR_PUBLISH(1) BIGR_PUBLISH(2) BIGR_PUBLISH(3)
@@ -293,6 +297,7 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
                 const int wkey = __reduce_max_sync(RST_FULL_MASK, part_key[par * NW + (tx & 15)]);
                 const int wp = 15 - ((wkey >> 3) & 15), ip = 7 - (wkey & 7);
                 const double rp = part_val[par * NW + wp];
+                const double *prow = slot + (par * NW + wp) * SLOTW + tx;
                 if (ty == wp) {
                     // the winning row leaves the panel: record it, stage it for the UEF store, clear its registers
                     if (tx == 0 && !(fabs(rp) <= 1.79769313486231570e308)) atomicOr(flags, RST_FLAG_ZERO_PIVOT);
@@ -302,6 +307,7 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
     case I:                                                                                         \
         if (I < RT) {                                                                               \
             st[I < RT ? I : 0] = k;                                                                 \
+            l[I < RT ? I : 0] = 0.0;                                                                \
             _Pragma("unroll") for (int j = jk; j < CT; ++j) su[32 * j * PU] = a[I < RT ? I : 0][j]; \
             _Pragma("unroll") for (int j = 0; j < CT; ++j) a[I < RT ? I : 0][j] = 0.0;              \
         }                                                                                           \
@@ -312,24 +318,19 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
                     }
                     act &= ~(1u << ip);
                 }
-                // multipliers of this warp's rows: the owner lane writes them into the Lm staging column k, which is
-                // also where the other lanes read them from
-                double *lcol = stage_l + k * PL + ty;
-                if (tx == kk) {
 #pragma unroll
-                    for (int i = 0; i < RT; ++i) lcol[16 * i] = a[i][jk] * rp;
+                for (int i = 0; i < RT; ++i) l[i] *= rp;
+                if (tx == kk) {   // multiplier column k -> Lm staging
+                    double *lcol = stage_l + k * PL + ty;
+#pragma unroll
+                    for (int i = 0; i < RT; ++i) lcol[16 * i] = l[i];
                 }
-                __syncwarp();
-                const double *prow = slot + (par * NW + wp) * SLOTW + tx;
-                double pr[CT];
 #pragma unroll
-                for (int j = jk; j < CT; ++j) pr[j] = prow[32 * j];
-                if (tx <= kk) pr[jk] = 0.0;   // columns <= k of this block are finished
+                for (int j = jk; j < CT; ++j) {
+                    double pr = prow[32 * j];
+                    if (j == jk && tx <= kk) pr = 0.0;   // columns <= k of this block are finished
 #pragma unroll
-                for (int i = 0; i < RT; ++i) {
-                    const double l = lcol[16 * i];
-#pragma unroll
-                    for (int j = jk; j < CT; ++j) a[i][j] = fma(-l, pr[j], a[i][j]);
+                    for (int i = 0; i < RT; ++i) a[i][j] = fma(-l[i], pr, a[i][j]);
                 }
             }
         }
@@ -523,8 +524,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
     }
 }
 
-constexpr int BIGP_KC = 16;      // elimination steps (forward) per stage
-constexpr int BIGP_NS = 4;       // ring depth
+constexpr int BIGP_KC = 8;       // elimination steps (forward) per stage
+constexpr int BIGP_NS = 3;       // ring depth
 constexpr int BIGP_THREADS = 128;
 __host__ __device__ inline size_t bigp_forward_smem(int nv) { return (size_t)BIGP_NS * BIGP_KC * 2 * nv * sizeof(double); }
 
@@ -610,7 +611,7 @@ __global__ void __launch_bounds__(BIGP_THREADS) bigp_forward_kernel(AbdLevel L, 
     if (pvr == 127) L.r_next[slab * nv + t_c] = w;
 }
 
-constexpr int BIGP_CC = 32;      // UEF rows (c) per stage in the backward sweep
+constexpr int BIGP_CC = 16;      // UEF rows (c) per stage in the backward sweep
 __host__ __device__ inline size_t bigp_backward_smem(int nv) { return (size_t)BIGP_NS * BIGP_CC * nv * sizeof(double); }
 
 // backward sweep: interior nodes of the slab from its end nodes.  Stage order per block row (descending):

@@ -132,6 +132,25 @@ int rst_b200_accept_trial(rst_b200_solver *s);
 /* device-side checkpoint of the state: restore == 0 saves Y, restore != 0 copies it back (no host traffic) */
 int rst_b200_checkpoint(rst_b200_solver *s, int restore);
 
+/* ---- adaptive grid refinement hand-off ------------------------------------------- */
+/* GridRefinementMethod (src/numerical/BVP_Damp/grid_api.rs:62-115); TwoPoint is not provided */
+#define RST_B200_GRID_DOUBLE_POINTS 0   /* refine_all_grid_par      adaptive_grid_basic.rs:187 */
+#define RST_B200_GRID_EASY 1            /* easy_grid_refinement_par :257, params = {tolerance} */
+#define RST_B200_GRID_PEARSON 2         /* pearson_grid_refinement_par :469, params = {d, C} */
+#define RST_B200_GRID_GRCAR_SMOOKE 3    /* grcar_smooke_grid_refinement :565, params = {d, g, C} */
+#define RST_B200_GRID_SCI 4             /* scipy_grid_refinement :885, uses abs_tolerance and the residual of the state */
+/* new_grid (grid_api.rs:154): marks, refined mesh and linearly interpolated full solution computed on the device from
+ * the CURRENT state; results stay in the handle.  n_added = number of inserted nodes (0 = "no new grid is needed"). */
+int rst_b200_new_grid(rst_b200_solver *s, int method, const double *params, double abs_tolerance,
+                      int64_t *n_points_new, int64_t *n_added);
+/* host copies of the last rst_b200_new_grid result (any pointer may be NULL): mesh [n_points_new], full solution
+ * [n_points_new * nv] node-major, marks [N + 1] */
+int rst_b200_new_grid_fetch(rst_b200_solver *s, double *mesh_out, size_t mesh_len, double *y_full_out, size_t y_len,
+                            int32_t *marks_out, size_t marks_len);
+/* try_solve_with_new_grid (NR_Damp_solver_damped.rs:2281-2340): a new handle on the refined mesh whose state is the
+ * interpolated solution (device to device); the caller continues with rst_b200_newton_solve and destroys the old handle */
+int rst_b200_create_refined(rst_b200_solver *s, rst_b200_solver **out);
+
 /* whole damped Newton loop (try_main_loop_damped, NR_Damp_solver_damped.rs:2027-2156) */
 int rst_b200_newton_solve(rst_b200_solver *s, const rst_b200_newton_opts *opts, rst_b200_newton_stats *stats);
 /* ONE iteration of that loop from the current state (bench step): recalc_jacobian != 0 forces a

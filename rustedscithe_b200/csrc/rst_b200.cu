@@ -22,6 +22,7 @@
 #include "btd.cuh"
 #include "p2p.cuh"
 #include "big.cuh"
+#include "grid.cuh"
 #include "assemble.cuh"
 #include "newton.cuh"
 #include "generated_problems.cuh"  // from the -I generated directory (default: csrc/generated)
@@ -353,6 +354,17 @@ struct rst_b200_solver {
     void *allgather_ctx = nullptr;
     int64_t launches = 0;
     cudaEvent_t ev[2]{};
+    // retained create() arguments (a refined-grid handle is created from them, rst_b200_create_refined)
+    std::vector<int> k_bc_var, k_bc_side;
+    std::vector<double> k_bc_val, k_params, k_lo, k_hi, k_rtol;
+    int k_slab = 0;
+    // adaptive grid refinement (grid.cuh): results of the last rst_b200_new_grid
+    int *g_mark[2] = {nullptr, nullptr};
+    int g_mark_cur = 0;
+    int64_t *g_pos = nullptr, *g_block_sum = nullptr, *g_total = nullptr;
+    unsigned long long *g_ext = nullptr;
+    double *g_mesh_new = nullptr, *g_Y_new = nullptr;
+    int64_t g_nodes_new = 0, g_added = -1;
 };
 
 // nv == 2 path with mapped peers: the interface exchange + solve is fused into the single-CTA tail kernels
@@ -457,6 +469,14 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
     s->scheme = d->scheme;
     s->trap_time = d->trap_time;
     s->device = d->device;
+    s->k_bc_var.assign(d->bc_var, d->bc_var + d->n_bc);
+    s->k_bc_side.assign(d->bc_side, d->bc_side + d->n_bc);
+    s->k_bc_val.assign(d->bc_val, d->bc_val + d->n_bc);
+    if (d->params && pb->np > 0) s->k_params.assign(d->params, d->params + pb->np);
+    s->k_lo.assign(d->lo, d->lo + nv);
+    s->k_hi.assign(d->hi, d->hi + nv);
+    s->k_rtol.assign(d->rtol, d->rtol + nv);
+    s->k_slab = d->slab;
     s->rank = d->rank;
     s->world = world;
     s->N = d->n_steps;
@@ -699,6 +719,7 @@ extern "C" int rst_b200_set_params(rst_b200_solver *s, const double *params, int
     if (s->np > 0) {
         CUDA_TRY(cudaMemcpyAsync(s->d_params, params, s->np * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
+        s->k_params.assign(params, params + s->np);
     }
     s->have_jac = s->factored = false;
     return RST_B200_OK;
@@ -713,6 +734,176 @@ extern "C" int rst_b200_dist_range(const rst_b200_solver *s, int64_t *b, int64_t
     if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
     if (b) *b = s->j_begin;
     if (e) *e = s->j_begin + s->n;
+    return RST_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// adaptive grid refinement hand-off (grid.cuh; reference: grid_api.rs:154, NR_Damp_solver_damped.rs:2202-2340)
+// ------------------------------------------------------------------------------------------------
+static void grid_free(rst_b200_solver *s, void *p) {
+    if (!p) return;
+    for (auto it = s->owned.begin(); it != s->owned.end(); ++it)
+        if (*it == p) { s->owned.erase(it); break; }
+    cudaFree(p);
+}
+
+extern "C" int rst_b200_new_grid(rst_b200_solver *s, int method, const double *params, double abs_tolerance,
+                                 int64_t *n_points_new, int64_t *n_added) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    if (s->world != 1) return fail(RST_B200_ERR_UNSUPPORTED, "grid refinement runs on the single-GPU path (regrid, then re-partition)");
+    if (method < RST_B200_GRID_DOUBLE_POINTS || method > RST_B200_GRID_SCI)
+        return fail(RST_B200_ERR_UNSUPPORTED, "grid refinement method not supported (TwoPoint is outside the hot-path scope)");
+    if (method != RST_B200_GRID_DOUBLE_POINTS && method != RST_B200_GRID_SCI && !params)
+        return fail(RST_B200_ERR_INVALID, "grid refinement parameters missing");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const int nv = s->nv;
+    const int64_t nn = s->n + 1;
+    cudaStream_t st = s->stream;
+    if (!s->g_mark[0]) {
+        TRY(dev_alloc(s, &s->g_mark[0], (size_t)nn));
+        TRY(dev_alloc(s, &s->g_mark[1], (size_t)nn));
+        TRY(dev_alloc(s, &s->g_pos, (size_t)nn));
+        TRY(dev_alloc(s, &s->g_block_sum, (size_t)((nn + GRID_SCAN_BLOCK - 1) / GRID_SCAN_BLOCK) + 1));
+        TRY(dev_alloc(s, &s->g_total, (size_t)1));
+        TRY(dev_alloc(s, &s->g_ext, (size_t)4 * nv));
+    }
+    GridArgs g{s->Y, s->uniform ? nullptr : s->d_mesh, s->t0, s->h, nn, nv};
+    const unsigned nb = (unsigned)((nn + 255) / 256);
+    int cur = 0;
+    if (method == RST_B200_GRID_DOUBLE_POINTS) {
+        grid_mark_all_kernel<<<nb, 256, 0, st>>>(s->g_mark[0], nn);
+        s->launches += 1;
+    } else if (method == RST_B200_GRID_SCI) {
+        // residual of the current (converged) state, as create_new_grid does (NR_Damp_solver_damped.rs:2235-2250)
+        TRY(rst_b200_eval_residual(s, 0));
+        unsigned *oob = s->d_flags + 1;
+        CUDA_TRY(cudaMemsetAsync(oob, 0, sizeof(unsigned), st));
+        const int64_t m_res = s->n * nv;
+        const int64_t nt = std::max(m_res, nn);
+        grid_mark_sci_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(s->F, m_res, abs_tolerance, s->g_mark[0], nn, oob);
+        s->launches += 1;
+        unsigned h_oob = 0;
+        CUDA_TRY(cudaMemcpyAsync(&h_oob, oob, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (h_oob)
+            return fail(RST_B200_ERR_INVALID, "Sci refinement: a residual row beyond the mesh length exceeds the tolerance "
+                                              "(the reference indexes the mesh with the residual row and panics here)");
+    } else {
+        // per-variable extrema of y and dy/dx
+        std::vector<unsigned long long> init((size_t)4 * nv);
+        for (int v = 0; v < nv; ++v) {
+            init[4 * v + 0] = init[4 * v + 2] = ~0ull;
+            init[4 * v + 1] = init[4 * v + 3] = 0ull;
+        }
+        CUDA_TRY(cudaMemcpyAsync(s->g_ext, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));   // `init` is a stack-owned staging buffer
+        int64_t want = std::min<int64_t>(nn * nv, (int64_t)148 * 8 * 256);
+        const int64_t step = ((want + nv - 1) / nv) * nv;
+        grid_extrema_kernel<<<(unsigned)((step + 255) / 256), 256, 0, st>>>(g, s->g_ext, step);
+        s->launches += 1;
+        if (method == RST_B200_GRID_EASY) {
+            grid_mark_easy_kernel<<<nb, 256, 0, st>>>(g, s->g_ext, params[0], s->g_mark[0]);
+            s->launches += 1;
+        } else {
+            const bool grcar = method == RST_B200_GRID_GRCAR_SMOOKE;
+            const double d = params[0], gp = grcar ? params[1] : 0.0, C = grcar ? params[2] : params[1];
+            CUDA_TRY(cudaMemsetAsync(s->g_mark[0], 0, (size_t)nn * sizeof(int), st));
+            for (int v = 0; v < nv; ++v) {   // the merge across variables is order dependent: one pass per variable
+                grid_mark_jump_kernel<<<nb, 256, 0, st>>>(g, s->g_ext, v, d, gp, grcar ? 1 : 0, s->g_mark[cur], s->g_mark[cur ^ 1]);
+                cur ^= 1;
+            }
+            grid_mark_buffer_kernel<<<nb, 256, 0, st>>>(g, C, s->g_mark[cur], s->g_mark[cur ^ 1]);
+            cur ^= 1;
+            s->launches += nv + 1;
+        }
+    }
+    s->g_mark_cur = cur;
+    const int64_t nblk = (nn + GRID_SCAN_BLOCK - 1) / GRID_SCAN_BLOCK;
+    grid_scan_local_kernel<<<(unsigned)nblk, GRID_SCAN_BLOCK, 0, st>>>(s->g_mark[cur], nn, s->g_pos, s->g_block_sum);
+    grid_scan_blocks_kernel<<<1, 32, 0, st>>>(s->g_block_sum, nblk, s->g_total);
+    grid_scan_add_kernel<<<(unsigned)nblk, GRID_SCAN_BLOCK, 0, st>>>(s->g_pos, nn, s->g_block_sum);
+    s->launches += 3;
+    int64_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, s->g_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    grid_free(s, s->g_mesh_new);
+    grid_free(s, s->g_Y_new);
+    s->g_mesh_new = s->g_Y_new = nullptr;
+    TRY(dev_alloc(s, &s->g_mesh_new, (size_t)total));
+    TRY(dev_alloc(s, &s->g_Y_new, (size_t)total * nv));
+    const int64_t ne = nn * nv;
+    grid_construct_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(g, s->g_mark[cur], s->g_pos, method == RST_B200_GRID_SCI ? 1 : 0,
+                                                                         s->g_mesh_new, s->g_Y_new);
+    s->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    s->g_nodes_new = total;
+    s->g_added = total - nn;
+    if (n_points_new) *n_points_new = total;
+    if (n_added) *n_added = total - nn;
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_new_grid_fetch(rst_b200_solver *s, double *mesh_out, size_t mesh_len, double *y_full_out, size_t y_len,
+                                       int32_t *marks_out, size_t marks_len) {
+    if (!s || s->g_added < 0) return fail(RST_B200_ERR_INVALID, "no refined grid: call rst_b200_new_grid first");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (mesh_out) {
+        if (mesh_len != (size_t)s->g_nodes_new) return fail(RST_B200_ERR_INVALID, "mesh buffer length mismatch");
+        CUDA_TRY(cudaMemcpyAsync(mesh_out, s->g_mesh_new, mesh_len * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (y_full_out) {
+        if (y_len != (size_t)s->g_nodes_new * s->nv) return fail(RST_B200_ERR_INVALID, "solution buffer length mismatch");
+        CUDA_TRY(cudaMemcpyAsync(y_full_out, s->g_Y_new, y_len * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (marks_out) {
+        if (marks_len != (size_t)(s->n + 1)) return fail(RST_B200_ERR_INVALID, "marks buffer length mismatch");
+        CUDA_TRY(cudaMemcpyAsync(marks_out, s->g_mark[s->g_mark_cur], marks_len * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return RST_B200_OK;
+}
+
+extern "C" int rst_b200_create_refined(rst_b200_solver *s, rst_b200_solver **out) {
+    if (!s || !out) return fail(RST_B200_ERR_INVALID, "null handle");
+    if (s->g_added < 0) return fail(RST_B200_ERR_INVALID, "no refined grid: call rst_b200_new_grid first");
+    CUDA_TRY(cudaSetDevice(s->device));
+    // the mesh is a create() argument (host); 8 bytes per node cross PCIe, the state stays on the device
+    std::vector<double> mesh((size_t)s->g_nodes_new);
+    CUDA_TRY(cudaMemcpyAsync(mesh.data(), s->g_mesh_new, mesh.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    rst_b200_desc d{};
+    d.problem_key = s->pb->key;
+    d.n_steps = s->g_nodes_new - 1;
+    d.scheme = s->scheme;
+    d.trap_time = s->trap_time;
+    d.t0 = mesh.front();
+    d.t_end = mesh.back();
+    d.mesh = mesh.data();
+    d.n_bc = (int)s->k_bc_var.size();
+    d.bc_var = s->k_bc_var.data();
+    d.bc_side = s->k_bc_side.data();
+    d.bc_val = s->k_bc_val.data();
+    d.params = s->k_params.empty() ? nullptr : s->k_params.data();
+    d.n_params = s->np;
+    d.lo = s->k_lo.data();
+    d.hi = s->k_hi.data();
+    d.rtol = s->k_rtol.data();
+    d.device = s->device;
+    d.stream = s->own_stream ? nullptr : (void *)s->stream;
+    d.slab = s->k_slab;
+    d.rank = 0;
+    d.world = 1;
+    rst_b200_solver *t = nullptr;
+    TRY(rst_b200_create(&d, &t));
+    cudaStreamSynchronize(t->stream);
+    // interpolated full solution -> state of the new handle (device to device); both streams drained around the copy
+    cudaError_t e = cudaMemcpyAsync(t->Y, s->g_Y_new, (size_t)s->g_nodes_new * s->nv * sizeof(double), cudaMemcpyDeviceToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) {
+        rst_b200_destroy(t);
+        return fail(RST_B200_ERR_CUDA, std::string("refined state copy: ") + cudaGetErrorString(e));
+    }
+    *out = t;
     return RST_B200_OK;
 }
 

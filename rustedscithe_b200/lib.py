@@ -84,6 +84,9 @@ SYMBOLS = {
     "rst_b200_make_trial": (C.c_int, [_H, C.c_double]),
     "rst_b200_accept_trial": (C.c_int, [_H]),
     "rst_b200_checkpoint": (C.c_int, [_H, C.c_int]),
+    "rst_b200_new_grid": (C.c_int, [_H, C.c_int, c_f64_p, C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "rst_b200_new_grid_fetch": (C.c_int, [_H, c_f64_p, C.c_size_t, c_f64_p, C.c_size_t, C.POINTER(C.c_int32), C.c_size_t]),
+    "rst_b200_create_refined": (C.c_int, [_H, C.POINTER(_H)]),
     "rst_b200_newton_solve": (C.c_int, [_H, C.POINTER(NewtonOpts), C.POINTER(NewtonStats)]),
     "rst_b200_newton_iterate": (C.c_int, [_H, C.POINTER(NewtonOpts), C.c_int, C.POINTER(NewtonStats)]),
     "rst_b200_newton_frozen": (C.c_int, [_H, C.POINTER(FrozenOpts), C.POINTER(NewtonStats)]),

@@ -18,11 +18,22 @@ from . import lib as _lib
 from . import problems as _problems
 
 
+GRID_METHODS = {"DoublePoints": 0, "Easy": 1, "Pearson": 2, "GrcarSmooke": 3, "Sci": 4}  # grid_api.rs:62-115
+
+
+@dataclass
+class AdaptiveGridConfig:  # NR_Damp_solver_damped.rs:115-122
+    version: int = 1
+    max_refinements: int = 3
+    grid_method: tuple = ("DoublePoints",)   # (GridRefinementMethod name, *parameters)
+
+
 @dataclass
 class SolverParams:  # NR_Damp_solver_damped.rs:100-151
     max_jac: int = 3
     max_damp_iter: int = 5
     damp_factor: float = 0.5
+    adaptive: AdaptiveGridConfig | None = None
 
 
 @dataclass
@@ -168,12 +179,67 @@ class NRBVP:
 
     # -- reference solver surface -----------------------------------------------------------
     def try_solve(self):
-        """try_solve -> try_main_loop_damped; returns the reduced solution or None (as the reference)."""
-        opts = self._opts()
-        rc = self.L.rst_b200_newton_solve(self.handle, C.byref(opts), C.byref(self.stats))
-        _lib.check(rc)
-        self.result = self.get_state() if self.stats.status == 1 else None
-        return self.result
+        """try_solve -> try_main_loop_damped (+ try_solve_with_new_grid when strategy_params.adaptive is set);
+        returns the reduced solution or None (as the reference)."""
+        adaptive = self.options.strategy_params.adaptive
+        new_grid_enabled = adaptive is not None                     # NR_Damp_solver_damped.rs:662-666
+        self.grid_refinements, self.nodes_added = 0, []
+        self.total_statistics = {"number of iterations": 0, "number of solving linear systems": 0,
+                                 "number of jacobians recalculations": 0, "number of grid refinements": 0}
+        self.result = None
+        while True:
+            opts = self._opts()
+            self._ck(self.L.rst_b200_newton_solve(self.handle, C.byref(opts), C.byref(self.stats)))
+            t = self.total_statistics
+            t["number of iterations"] += self.stats.iterations
+            t["number of solving linear systems"] += self.stats.linear_solves
+            t["number of jacobians recalculations"] += self.stats.jac_recalcs
+            if self.stats.status != 1:
+                # the reference would refine from the last converged result here (:2145-2154); without one it has
+                # nothing to refine -- a failed solve ends the adaptive loop
+                self.result = None if self.grid_refinements == 0 else self.result
+                return None
+            self.result = self.get_state()
+            if not (new_grid_enabled and adaptive is not None):      # :2102-2113
+                return self.result
+            # ---- try_solve_with_new_grid (:2281-2340) ----
+            if adaptive.version != 1:
+                raise ValueError("unsupported adaptive version")    # we_need_refinement panics (:2182)
+            name, *gp = adaptive.grid_method
+            _, n_added = self.new_grid(name, gp, fetch=False)
+            self.grid_refinements += 1
+            self.nodes_added.append(n_added)
+            t["number of grid refinements"] += 1
+            new_grid_enabled = (n_added != 0) and not (adaptive.max_refinements <= self.grid_refinements)  # :2164-2196
+            if n_added == 0:
+                return None                                          # "no new grid needed" returns Ok(None) (:2333-2336)
+            self._adopt_refined()
+
+    def new_grid(self, method, params=(), fetch=True):
+        """new_grid (grid_api.rs:154) on the CURRENT device state.  Returns (n_points_new, n_added) or, with fetch,
+        (mesh, full solution (n_points_new x nv), n_added, marks)."""
+        m = GRID_METHODS[method] if isinstance(method, str) else int(method)
+        p = _f64(list(params) + [0.0] * (3 - len(params)))
+        n_new, n_added = C.c_int64(), C.c_int64()
+        self._ck(self.L.rst_b200_new_grid(self.handle, m, _p(p), self.options.abs_tolerance, C.byref(n_new), C.byref(n_added)))
+        if not fetch:
+            return n_new.value, n_added.value
+        mesh = np.zeros(n_new.value)
+        yfull = np.zeros(n_new.value * self.nv)
+        marks = np.zeros(self.n_steps + 1, dtype=np.int32)
+        self._ck(self.L.rst_b200_new_grid_fetch(self.handle, _p(mesh), mesh.shape[0], _p(yfull), yfull.shape[0],
+                                                 marks.ctypes.data_as(C.POINTER(C.c_int32)), marks.shape[0]))
+        return mesh, yfull.reshape(n_new.value, self.nv), n_added.value, marks
+
+    def _adopt_refined(self):
+        """Continue on the refined mesh: new handle, state = interpolated solution (stays on the device)."""
+        new = C.c_void_p()
+        self._ck(self.L.rst_b200_create_refined(self.handle, C.byref(new)))
+        n_new, _ = C.c_int64(), None
+        self.L.rst_b200_destroy(self.handle)
+        self.handle = new
+        self.n = int(self.L.rst_b200_n_unknowns(self.handle))
+        self.n_steps = self.n // self.nv
 
     def try_solve_frozen(self, strategy="Frozen_naive", strategy_params=(), tolerance=1e-6, max_iterations=25):
         """Frozen-Jacobian Newton (NR_Damp_solver_frozen.rs: NRBVP::try_solve with FrozenSolverOptions)."""
@@ -202,6 +268,7 @@ class NRBVP:
         s = self.stats
         return {"number of iterations": s.iterations, "number of solving linear systems": s.linear_solves,
                 "number of jacobians recalculations": s.jac_recalcs, "factorizations": s.factorizations,
+                "number of grid refinements": getattr(self, "grid_refinements", 0),
                 "status": s.status, "ms_total": s.ms_total}
 
     # -- Fun / Jac callbacks through the reference's AOT ABI (host pointers) -----------------

@@ -161,22 +161,28 @@ __global__ void __launch_bounds__(BIG_THREADS) big_factor_kernel(AbdLevel L, int
 // and written with coalesced stores in the layout of abd.cuh (Lm [g][k][row], UEF [g][c][k]), so the sweeps and the
 // narrow-block kernels read the same factors.  FP64-pipe bound: 48 DFMA per thread and step.
 // ------------------------------------------------------------------------------------------------
-template <int NVP>
+// NW = 16: 8 x 6 tile per thread, pivot rows staged in smem for a coalesced UEF store.
+// NW = 32: 4 x 6 tile per thread (64 registers, twice the warps to hide the latency of the per-step chain), pivot rows
+//          stored straight to global (the L2 merges the four 8-byte words of a sector written by consecutive steps).
+template <int NVP, int NW_>
 struct BigrCfg {
-    static constexpr int RT = NVP / 8, CT = 3 * NVP / 32, JB = NVP / 32, WARPS = 16, THREADS = 512;
+    static constexpr int WARPS = NW_, THREADS = 32 * NW_;
+    static constexpr int RT = 2 * NVP / WARPS, CT = 3 * NVP / 32, JB = NVP / 32;
+    static constexpr bool DIRECT_U = NW_ > 16;
     static constexpr int SLOTW = 3 * NVP;                       // padded panel width
     static constexpr int PU = NVP + 1;                          // stage_u[c_padded][k] pitch
     static constexpr int PL = 2 * NVP + 1;                      // stage_l[k][row] pitch
     static constexpr int slot_doubles = 2 * WARPS * SLOTW;
-    static constexpr int stage_u_doubles = SLOTW * PU;
+    static constexpr int stage_u_doubles = DIRECT_U ? 0 : SLOTW * PU;
     static constexpr int stage_l_doubles = NVP * PL;
     static constexpr size_t smem_bytes = (size_t)(slot_doubles + stage_u_doubles + stage_l_doubles + 2 * WARPS) * sizeof(double) +
                                          (2 * WARPS + 2 * NVP + 8) * sizeof(int) + 2 * NVP;
 };
 
-template <int NVP, bool IDENT_B>
-__global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv, unsigned *flags) {
-    using C = BigrCfg<NVP>;
+template <int NVP, int NW_, bool IDENT_B>
+__global__ void __launch_bounds__(32 * NW_, 1) bigr_factor_kernel(AbdLevel L, int nv, unsigned *flags) {
+    using C = BigrCfg<NVP, NW_>;
+    static_assert(C::RT >= 1 && C::RT <= 8, "rows per thread");
     constexpr int RT = C::RT, CT = C::CT, JB = C::JB, SLOTW = C::SLOTW, PU = C::PU, PL = C::PL, NW = C::WARPS;
     extern __shared__ __align__(16) unsigned char big_smem[];
     double *slot = reinterpret_cast<double *>(big_smem);                 // [2][16][SLOTW] candidate rows
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
     unsigned act = 0;   // bit i: st[i] == ACTIVE
 #pragma unroll
     for (int i = 0; i < RT; ++i) {
-        const int r = ty + 16 * i;
+        const int r = ty + NW * i;
 #pragma unroll
         for (int j = 0; j < CT; ++j) a[i][j] = 0.0;
         st[i] = r < nv ? ACTIVE : (r < R2 ? 0 : DEAD);
@@ -218,14 +224,15 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
     }
     // keys: |pivot| high word with the low 7 bits replaced by (15 - warp, 7 - row) -> ties go to the lowest row; the
     // pivot is the largest candidate up to 2^-13 relative, i.e. threshold pivoting with a threshold of 0.9999
-    const int keytag = ((15 - ty) << 3);
+    const int keytag = ((NW - 1 - ty) << 3);
+    constexpr int KEYMASK = NW > 16 ? 0x7fffff00 : 0x7fffff80;
 
     for (int istep = 1; istep < len; ++istep) {
         const int64_t g = g0 + istep;
         // ---- new block row t goes into the t-th free row (ascending), as the sweeps assume ----
         if (tx == 0) {
 #pragma unroll
-            for (int i = 0; i < RT; ++i) s_pv[ty + 16 * i] = (unsigned char)st[i];
+            for (int i = 0; i < RT; ++i) s_pv[ty + NW * i] = (unsigned char)st[i];
         }
         __syncthreads();
         if (tid < 2 * NVP) {
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < RT; ++i) {
-            const int t = tmap[ty + 16 * i];
+            const int t = tmap[ty + NW * i];
             if (t >= 0) {
                 st[i] = ACTIVE;
                 act |= 1u << i;
@@ -267,7 +274,7 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
                 // warp-local candidate of column k (held by lane kk in register column jk)
                 int key = -1;
 #pragma unroll
-                for (int i = 0; i < RT; ++i) key = max(key, ((__double2hiint(a[i][jk]) & 0x7fffff80) | keytag) + (7 - i));
+                for (int i = 0; i < RT; ++i) key = max(key, ((__double2hiint(a[i][jk]) & KEYMASK) | keytag) + (7 - i));
                 key = __shfl_sync(RST_FULL_MASK, key, kk);
                 // column k of this warp's rows, broadcast to every lane (becomes the multipliers after the barrier)
                 double l[RT];
@@ -294,21 +301,29 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
                 }
                 __syncthreads();
                 // winner over the 16 warps
-                const int wkey = __reduce_max_sync(RST_FULL_MASK, part_key[par * NW + (tx & 15)]);
-                const int wp = 15 - ((wkey >> 3) & 15), ip = 7 - (wkey & 7);
+                const int wkey = __reduce_max_sync(RST_FULL_MASK, part_key[par * NW + (tx & (NW - 1))]);
+                const int wp = NW - 1 - ((wkey >> 3) & (NW - 1)), ip = 7 - (wkey & 7);
                 const double rp = part_val[par * NW + wp];
                 const double *prow = slot + (par * NW + wp) * SLOTW + tx;
                 if (ty == wp) {
                     // the winning row leaves the panel: record it, stage it for the UEF store, clear its registers
                     if (tx == 0 && !(fabs(rp) <= 1.79769313486231570e308)) atomicOr(flags, RST_FLAG_ZERO_PIVOT);
-                    double *su = stage_u + tx * PU + k;
+                    // pivot row k -> UEF [c][k]: staged for a coalesced store, or straight to global (DIRECT_U)
+                    double *su = C::DIRECT_U ? L.UEF + g * (int64_t)(3 * nv * nv) + k : stage_u + tx * PU + k;
                     switch (ip) {
 #define BIGR_RETIRE(I)                                                                              \
     case I:                                                                                         \
         if (I < RT) {                                                                               \
             st[I < RT ? I : 0] = k;                                                                 \
             l[I < RT ? I : 0] = 0.0;                                                                \
-            _Pragma("unroll") for (int j = jk; j < CT; ++j) su[32 * j * PU] = a[I < RT ? I : 0][j]; \
+            _Pragma("unroll") for (int j = jk; j < CT; ++j) {                                       \
+                if (C::DIRECT_U) {                                                                  \
+                    const int cc = tx + 32 * (j % JB);                                              \
+                    if (cc < nv) su[((j / JB) * nv + cc) * nv] = a[I < RT ? I : 0][j];              \
+                } else {                                                                            \
+                    su[32 * j * PU] = a[I < RT ? I : 0][j];                                         \
+                }                                                                                   \
+            }                                                                                       \
             _Pragma("unroll") for (int j = 0; j < CT; ++j) a[I < RT ? I : 0][j] = 0.0;              \
         }                                                                                           \
         break;
@@ -323,7 +338,7 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
                 if (tx == kk) {   // multiplier column k -> Lm staging
                     double *lcol = stage_l + k * PL + ty;
 #pragma unroll
-                    for (int i = 0; i < RT; ++i) lcol[16 * i] = l[i];
+                    for (int i = 0; i < RT; ++i) lcol[NW * i] = l[i];
                 }
 #pragma unroll
                 for (int j = jk; j < CT; ++j) {
@@ -337,13 +352,15 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
         __syncthreads();
         // ---- factors of this block row (layout of abd.cuh): UEF [c][k], Lm [k][row], piv ----
         {
-            double *uef = L.UEF + g * (int64_t)(3 * nv * nv);
-            for (int b = 0; b < 3; ++b)
-                for (int cc = ty; cc < nv; cc += NW) {
-                    const double *src = stage_u + (b * NVP + cc) * PU;
-                    double *dst = uef + (b * nv + cc) * nv;
-                    for (int k = tx; k < nv; k += 32) st_cs(dst + k, src[k]);
-                }
+            if (!C::DIRECT_U) {
+                double *uef = L.UEF + g * (int64_t)(3 * nv * nv);
+                for (int b = 0; b < 3; ++b)
+                    for (int cc = ty; cc < nv; cc += NW) {
+                        const double *src = stage_u + (b * NVP + cc) * PU;
+                        double *dst = uef + (b * nv + cc) * nv;
+                        for (int k = tx; k < nv; k += 32) st_cs(dst + k, src[k]);
+                    }
+            }
             double *lm = L.Lm + g * (int64_t)(nv * R2);
             for (int k = ty; k < nv; k += NW)
                 for (int r = tx; r < R2; r += 32) st_cs(lm + k * R2 + r, stage_l[k * PL + r]);
@@ -351,7 +368,7 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
         if (tx == 0) {
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
-                const int r = ty + 16 * i;
+                const int r = ty + NW * i;
                 if (r < R2) L.piv[g * R2 + r] = (int8_t)st[i];
             }
         }
@@ -371,7 +388,7 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
     // ---- condensed row of the slab: carried rows in ascending order ----
     if (tx == 0) {
 #pragma unroll
-        for (int i = 0; i < RT; ++i) s_pv[ty + 16 * i] = (unsigned char)st[i];
+        for (int i = 0; i < RT; ++i) s_pv[ty + NW * i] = (unsigned char)st[i];
     }
     __syncthreads();
     if (tid < 2 * NVP) {
@@ -387,7 +404,7 @@ __global__ void __launch_bounds__(512, 1) bigr_factor_kernel(AbdLevel L, int nv,
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < RT; ++i) {
-        const int t = tmap[ty + 16 * i];
+        const int t = tmap[ty + NW * i];
         if (t >= 0) {
 #pragma unroll
             for (int j = 0; j < JB; ++j) {

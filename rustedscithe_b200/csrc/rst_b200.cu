@@ -193,24 +193,28 @@ struct SolverImpl {
 
 // wide blocks (16 < nv <= 64, or any nv >= 3 with RST_B200_FORCE_BIG): run-time-nv block-per-slab kernels (big.cuh)
 struct BigImpl {
-    template <int NVP>
+    template <int NVP, int NW>
     static void factor_tiled(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
-        using C = BigrCfg<NVP>;
+        using C = BigrCfg<NVP, NW>;
         static bool attr_set = false;
         if (!attr_set) {
-            cudaFuncSetAttribute(bigr_factor_kernel<NVP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
-            cudaFuncSetAttribute(bigr_factor_kernel<NVP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
+            cudaFuncSetAttribute(bigr_factor_kernel<NVP, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
+            cudaFuncSetAttribute(bigr_factor_kernel<NVP, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
             attr_set = true;
         }
-        if (ident_b) bigr_factor_kernel<NVP, true><<<(unsigned)L.nslabs, C::THREADS, C::smem_bytes, st>>>(L, L.nv, flags);
-        else bigr_factor_kernel<NVP, false><<<(unsigned)L.nslabs, C::THREADS, C::smem_bytes, st>>>(L, L.nv, flags);
+        if (ident_b) bigr_factor_kernel<NVP, NW, true><<<(unsigned)L.nslabs, C::THREADS, C::smem_bytes, st>>>(L, L.nv, flags);
+        else bigr_factor_kernel<NVP, NW, false><<<(unsigned)L.nslabs, C::THREADS, C::smem_bytes, st>>>(L, L.nv, flags);
     }
     static void factor(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
         // default: register-tiled panel (FP64-pipe bound); RST_B200_BIG_V1 selects the first shared-memory-panel kernel
         static const bool v1 = std::getenv("RST_B200_BIG_V1") != nullptr;
         if (!v1) {
-            if (L.nv <= 32) factor_tiled<32>(L, ident_b, flags, st);
-            else factor_tiled<64>(L, ident_b, flags, st);
+            // RST_B200_BIG_W32: 32 warps x (4 x 6) tile at 64 registers instead of 16 warps x (8 x 6) at 128 -- measured
+            // SLOWER (185 vs 112 ms per 2.5e5 rows: spills + uncoalesced pivot-row stores), kept for experiments
+            static const bool w32 = std::getenv("RST_B200_BIG_W32") != nullptr;
+            if (L.nv <= 32) factor_tiled<32, 16>(L, ident_b, flags, st);
+            else if (w32) factor_tiled<64, 32>(L, ident_b, flags, st);
+            else factor_tiled<64, 16>(L, ident_b, flags, st);
             return;
         }
         const size_t smem = big_factor_smem_bytes(L.nv);

@@ -297,7 +297,9 @@ __global__ void __launch_bounds__(32 * NW_, 1) bigr_factor_kernel(AbdLevel L, in
                 }
                 if (tx == kk) {
                     part_key[par * NW + ty] = key;
-                    part_val[par * NW + ty] = 1.0 / cand;      // reciprocal of the candidate pivot (inf when it is 0)
+                    // reciprocal of the candidate pivot; a zero candidate (sparse column: only zeros in this warp's rows) must not
+                    // enter the division's slow path
+                    part_val[par * NW + ty] = cand != 0.0 ? 1.0 / cand : __longlong_as_double(0x7ff0000000000000ll);
                 }
                 __syncthreads();
                 // winner over the 16 warps

@@ -207,11 +207,11 @@ struct BigImpl {
     }
     static void factor(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
         // default: register-tiled panel (FP64-pipe bound); RST_B200_BIG_V1 selects the first shared-memory-panel kernel
-        static const bool v1 = std::getenv("RST_B200_BIG_V1") != nullptr;
+        const bool v1 = std::getenv("RST_B200_BIG_V1") != nullptr;   // read per call: tests toggle it
         if (!v1) {
             // RST_B200_BIG_W32: 32 warps x (4 x 6) tile at 64 registers instead of 16 warps x (8 x 6) at 128 -- measured
             // SLOWER (185 vs 112 ms per 2.5e5 rows: spills + uncoalesced pivot-row stores), kept for experiments
-            static const bool w32 = std::getenv("RST_B200_BIG_W32") != nullptr;
+            const bool w32 = std::getenv("RST_B200_BIG_W32") != nullptr;
             if (L.nv <= 32) factor_tiled<32, 16>(L, ident_b, flags, st);
             else if (w32) factor_tiled<64, 32>(L, ident_b, flags, st);
             else factor_tiled<64, 16>(L, ident_b, flags, st);
@@ -230,7 +230,7 @@ struct BigImpl {
     // sweeps: generation 2 streams the factors through a shared-memory ring with bulk async copies (needs 16-byte
     // aligned stages, i.e. even nv); RST_B200_BIG_V1 or odd nv select the first kernels
     static bool pipelined(int nv) {
-        static const bool v1 = std::getenv("RST_B200_BIG_V1") != nullptr;
+        const bool v1 = std::getenv("RST_B200_BIG_V1") != nullptr;   // read per call: tests toggle it
         return !v1 && (nv % 2 == 0);
     }
     static void forward(const AbdLevel &L, cudaStream_t st) {

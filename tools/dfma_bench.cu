@@ -33,6 +33,30 @@ int main() {
         printf("warps/SM %2d: %.2f TFMA/s = %.2f TFLOP/s, %.1f DFMA/clk/SM at 1.965 GHz\n", warps, fma / ms / 1e9, 2 * fma / ms / 1e9,
                fma / (ms * 1e-3) / 148 / 1.965e9);
     }
+    {   // dependent-issue latency: one warp per SM, one accumulator
+        const int iters = 200000;
+        dfma_kernel<1><<<148, 32>>>(out, 100, 0.999);
+        cudaEventRecord(e0);
+        dfma_kernel<1><<<148, 32>>>(out, iters, 0.999);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("dependent DFMA latency: %.1f cycles at 1.965 GHz\n", ms * 1e-3 * 1.965e9 / iters);
+        dfma_kernel<2><<<148, 32>>>(out, iters, 0.999);
+        cudaEventRecord(e0);
+        dfma_kernel<2><<<148, 32>>>(out, iters, 0.999);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf("2 independent DFMA per iteration: %.1f cycles per iteration\n", ms * 1e-3 * 1.965e9 / iters);
+        dfma_kernel<8><<<148, 32>>>(out, iters, 0.999);
+        cudaEventRecord(e0);
+        dfma_kernel<8><<<148, 32>>>(out, iters, 0.999);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf("8 independent DFMA per iteration (1 warp): %.1f cycles per iteration\n", ms * 1e-3 * 1.965e9 / iters);
+    }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }

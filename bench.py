@@ -340,12 +340,15 @@ def main():
 
         reps = max(5, min(50, args.steps))
         phases = {}
+        regrid_ms = None
         if world == 1:
             phases["assemble_FJ"] = time_phase(lambda: solver.eval_jacobian(0), reps)
             phases["assemble_F"] = time_phase(lambda: solver.eval_residual(0), reps)
             solver.eval_jacobian(0)
             phases["factor"] = time_phase(lambda: solver.factor(), reps)
             phases["solve"] = time_phase(lambda: solver.solve(), reps)
+            # adaptive-grid hand-off on the current state (marks + scan + refined mesh + interpolated state, all on the device)
+            regrid_ms = time_phase(lambda: solver.new_grid("Pearson", (1e-3, 1.4), fetch=False), 3)
         peak, peak_src = _peaks()
         alg = {  # algorithmic bytes per interval, SURVEY.md section 8(d)
             "assemble_FJ": 8 * (2 * nv + nv * nv), "assemble_F": 8 * 2 * nv,
@@ -405,6 +408,8 @@ def main():
                         "d2h_bytes_per_step": bytes_local + 40 * per_solve["linear_solves"]},
                 "gpu_launches": int(launches),
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+                "regrid": None if regrid_ms is None else {"method": "Pearson(1e-3, 1.4)", "ms": regrid_ms,
+                                                           "note": "rst_b200_new_grid on the device-resident state"},
                 "jacobian_refresh_every_iteration": {"value": (1 if strong else world) * 1000.0 / refresh_ms, "unit": "iter/s",
                                                      "ms_per_iteration": refresh_ms},
             }

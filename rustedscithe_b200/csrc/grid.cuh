@@ -44,15 +44,18 @@ __host__ __device__ inline double ord_decode(unsigned long long e) {
 #endif
 }
 
-// ext[v][0..3] = encoded (min y, max y, min dy/dx, max dy/dx) of variable v; initialise with ~0 / 0 before the launch
+__global__ void grid_extrema_init_kernel(unsigned long long *ext, int nv) {
+    for (int i = threadIdx.x; i < 4 * nv; i += blockDim.x) ext[i] = (i & 1) ? 0ull : ~0ull;   // min slots ~0, max slots 0
+}
+
+// ext[v][0..3] = encoded (min y, max y, min dy/dx, max dy/dx) of variable v (grid_extrema_init_kernel first)
 __global__ void __launch_bounds__(256) grid_extrema_kernel(GridArgs g, unsigned long long *ext, int64_t step) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = g.n_nodes * g.nv;
-    if (tid >= step) return;
     const int v = (int)(tid % g.nv);   // step is a multiple of nv: a thread stays on one variable
     double ymin = 0, ymax = 0, smin = 0, smax = 0;
     bool have = false, have_s = false;
-    for (int64_t idx = tid; idx < total; idx += step) {
+    for (int64_t idx = tid; tid < step && idx < total; idx += step) {
         const int64_t i = idx / g.nv;
         const double y = g.Y[idx];
         if (!have) { ymin = ymax = y; have = true; }
@@ -64,13 +67,22 @@ __global__ void __launch_bounds__(256) grid_extrema_kernel(GridArgs g, unsigned 
             else { smin = fmin(smin, s); smax = fmax(smax, s); }
         }
     }
+    // block-level combine in shared memory first: a few hundred thousand threads on 4 nv global addresses would serialise
+    __shared__ unsigned long long sm[4 * 64];
+    for (int i = threadIdx.x; i < 4 * g.nv; i += blockDim.x) sm[i] = (i & 1) ? 0ull : ~0ull;
+    __syncthreads();
     if (have) {
-        atomicMin(ext + 4 * v + 0, ord_encode(ymin));
-        atomicMax(ext + 4 * v + 1, ord_encode(ymax));
+        atomicMin(sm + 4 * v + 0, ord_encode(ymin));
+        atomicMax(sm + 4 * v + 1, ord_encode(ymax));
     }
     if (have_s) {
-        atomicMin(ext + 4 * v + 2, ord_encode(smin));
-        atomicMax(ext + 4 * v + 3, ord_encode(smax));
+        atomicMin(sm + 4 * v + 2, ord_encode(smin));
+        atomicMax(sm + 4 * v + 3, ord_encode(smax));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * g.nv; i += blockDim.x) {
+        if (i & 1) atomicMax(ext + i, sm[i]);
+        else atomicMin(ext + i, sm[i]);
     }
 }
 

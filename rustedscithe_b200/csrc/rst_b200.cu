@@ -368,7 +368,7 @@ struct rst_b200_solver {
     int64_t *g_pos = nullptr, *g_block_sum = nullptr, *g_total = nullptr;
     unsigned long long *g_ext = nullptr;
     double *g_mesh_new = nullptr, *g_Y_new = nullptr;
-    int64_t g_nodes_new = 0, g_added = -1;
+    int64_t g_nodes_new = 0, g_added = -1, g_capacity = 0;
 };
 
 // nv == 2 path with mapped peers: the interface exchange + solve is fused into the single-CTA tail kernels
@@ -794,13 +794,7 @@ extern "C" int rst_b200_new_grid(rst_b200_solver *s, int method, const double *p
                                               "(the reference indexes the mesh with the residual row and panics here)");
     } else {
         // per-variable extrema of y and dy/dx
-        std::vector<unsigned long long> init((size_t)4 * nv);
-        for (int v = 0; v < nv; ++v) {
-            init[4 * v + 0] = init[4 * v + 2] = ~0ull;
-            init[4 * v + 1] = init[4 * v + 3] = 0ull;
-        }
-        CUDA_TRY(cudaMemcpyAsync(s->g_ext, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaStreamSynchronize(st));   // `init` is a stack-owned staging buffer
+        grid_extrema_init_kernel<<<1, 256, 0, st>>>(s->g_ext, nv);
         int64_t want = std::min<int64_t>(nn * nv, (int64_t)148 * 8 * 256);
         const int64_t step = ((want + nv - 1) / nv) * nv;
         grid_extrema_kernel<<<(unsigned)((step + 255) / 256), 256, 0, st>>>(g, s->g_ext, step);
@@ -830,11 +824,16 @@ extern "C" int rst_b200_new_grid(rst_b200_solver *s, int method, const double *p
     int64_t total = 0;
     CUDA_TRY(cudaMemcpyAsync(&total, s->g_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    grid_free(s, s->g_mesh_new);
-    grid_free(s, s->g_Y_new);
-    s->g_mesh_new = s->g_Y_new = nullptr;
-    TRY(dev_alloc(s, &s->g_mesh_new, (size_t)total));
-    TRY(dev_alloc(s, &s->g_Y_new, (size_t)total * nv));
+    if (total > s->g_capacity) {   // grow-only buffers: cudaMalloc / cudaFree cost milliseconds and synchronise the device
+        grid_free(s, s->g_mesh_new);
+        grid_free(s, s->g_Y_new);
+        s->g_mesh_new = s->g_Y_new = nullptr;
+        s->g_capacity = 0;
+        const int64_t cap = total + total / 4;
+        TRY(dev_alloc(s, &s->g_mesh_new, (size_t)cap));
+        TRY(dev_alloc(s, &s->g_Y_new, (size_t)cap * nv));
+        s->g_capacity = cap;
+    }
     const int64_t ne = nn * nv;
     grid_construct_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(g, s->g_mark[cur], s->g_pos, method == RST_B200_GRID_SCI ? 1 : 0,
                                                                          s->g_mesh_new, s->g_Y_new);

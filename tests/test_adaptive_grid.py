@@ -276,3 +276,57 @@ def test_gpu_adaptive_solve_matches_the_oracle_loop(key, n_steps, method, max_re
         else:
             assert out is None                # "no new grid needed" returns Ok(None); the result stays in `result`
     g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_new_grid_error_behaviour():
+    """Argument checking of the C ABI: unknown / unsupported method (TwoPoint), missing parameters, fetch before new_grid,
+    buffer length mismatches, and the Sci case in which the reference itself panics (residual row index past the mesh)."""
+    import ctypes as C
+    from rustedscithe_b200 import lib as rlib
+    key, n_steps = "combustion6", 20
+    spec = problems.get(key)
+    g = _gpu_solver(key, n_steps)
+    g.set_state(spec.guess(n_steps))
+    n_new, n_added = C.c_int64(), C.c_int64()
+    for method in (5, -1, 17):                    # 5 would be TwoPoint
+        rc = g.L.rst_b200_new_grid(g.handle, method, None, 1e-6, C.byref(n_new), C.byref(n_added))
+        assert rc == rlib.ERR_UNSUPPORTED
+    assert g.L.rst_b200_new_grid(g.handle, 2, None, 1e-6, C.byref(n_new), C.byref(n_added)) == rlib.ERR_INVALID
+    buf = np.zeros(4)
+    assert g.L.rst_b200_new_grid_fetch(g.handle, buf.ctypes.data_as(rlib.c_f64_p), 4, None, 0, None, 0) == rlib.ERR_INVALID
+    out = C.c_void_p()
+    assert g.L.rst_b200_create_refined(g.handle, C.byref(out)) == rlib.ERR_INVALID      # nothing to refine from yet
+    g.new_grid("DoublePoints", fetch=False)
+    assert g.L.rst_b200_new_grid_fetch(g.handle, buf.ctypes.data_as(rlib.c_f64_p), 4, None, 0, None, 0) == rlib.ERR_INVALID
+    # Sci with the flat start: residual rows far beyond the mesh length exceed the tolerance -> the reference panics
+    with pytest.raises(rlib.RstB200Error) as e:
+        g.new_grid("Sci")
+    assert e.value.code == rlib.ERR_INVALID
+    g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_refined_handle_is_a_full_solver():
+    """After the hand-off the new handle owns the refined mesh: residual / Jacobian / linear solve agree with an oracle
+    built on the fetched mesh, and the state is the interpolated solution."""
+    key, n_steps = "flame12", 48
+    spec = problems.get(key)
+    g = _gpu_solver(key, n_steps)
+    g.set_state(spec.guess(n_steps))
+    assert g.try_solve() is not None
+    mesh, y_new, n_added, _ = g.new_grid("GrcarSmooke", (0.05, 0.05, 1.5))
+    assert n_added > 0
+    g._adopt_refined()
+    assert g.n_steps == len(mesh) - 1
+    o = orc.OracleBVP(key, g.n_steps, spec.bc_list(), t0=spec.t0, t_end=spec.t_end, mesh=mesh)
+    y_red = y_new.reshape(-1)[o.unknown_pos]
+    assert np.array_equal(g.get_state(), y_red)
+    assert np.array_equal(g.get_result(), y_new)
+    r_ref = o.residual(y_red)
+    g.eval_jacobian()
+    g.factor()
+    dy = g.solve_in_place(r_ref)
+    dy_ref = o.solve_banded(o.jacobian_values(y_red), r_ref)
+    assert np.linalg.norm(dy - dy_ref) / np.linalg.norm(dy_ref) < 1e-10
+    g.close()

@@ -37,6 +37,7 @@ struct AbdLevel {
     int64_t nslabs;    // ceil(n / S) = block rows of the next level
     int S;             // slab length (rows per slab)
     int nv;            // block size (used by the run-time-nv kernels of big.cuh)
+    int prefetch;      // != 0: small (latency-bound) level, the sweeps prefetch the next block row's factors into L2
     const double *A;   // [n][nv][nv] row-major
     const double *B;   // [n][nv][nv] or nullptr (identity)
     double *A_next;    // [nslabs][nv][nv]
@@ -214,6 +215,8 @@ __global__ void __launch_bounds__(128) abd_forward_kernel(AbdLevel L) {
         const int64_t g = g0 + i;
         const bool is_free = row_ok && !carry;
         const unsigned fb = group_bits<G>(__ballot_sync(RST_FULL_MASK, is_free), gw);
+        if (L.prefetch && i + 1 < len && r * 128 < NV * R2 * 8)   // upper levels: one dependent DRAM round trip per block row
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(L.Lm + (g + 1) * (int64_t)(NV * R2)) + r * 128));
         int pv = -1;
         double lrow[NV];
 #pragma unroll
@@ -277,6 +280,11 @@ __global__ void __launch_bounds__(128) abd_backward_kernel(AbdLevel L) {
         double t = 0.0, inv = 1.0;
 #pragma unroll
         for (int c = 0; c < NV; ++c) U[c] = 0.0;
+        if (L.prefetch && slab_ok && i - 1 >= 1) {
+            const char *nx = reinterpret_cast<const char *>(L.UEF + (g - 1) * (int64_t)(3 * NV * NV));
+            for (int off = (lane & (G - 1)) * 128; off < 3 * NV * NV * 8; off += G * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + off));
+        }
         if (active && k_ok) {
             const double *u = L.UEF + g * (int64_t)(3 * NV * NV) + k;
             t = L.e[g * NV + k];

@@ -372,6 +372,12 @@ struct rst_b200_solver {
 };
 
 // nv == 2 path with mapped peers: the interface exchange + solve is fused into the single-CTA tail kernels
+// threads per CTA of the thread-per-slab kernels.  Small CTAs: the kernels hoist all loads of a slab, so a CTA runs in
+// phases (load burst -> dependent chain -> stores); few big CTAs per SM move through them in lock-step and leave HBM idle.
+static int tps_block() {
+    static const int b = [] { const char *e = std::getenv("RST_B200_TPS_BLOCK"); const int v = e ? std::atoi(e) : 64; return (v == 32 || v == 64 || v == 128) ? v : 64; }();
+    return b;
+}
 static bool fused_p2p(const rst_b200_solver *s) { return s->use_tps && s->p2p_enabled && s->world > 1; }
 
 static P2pIface iface_args(const rst_b200_solver *s, bool fused) {
@@ -674,7 +680,7 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
         s->red_blocks = 148 * 4;
         {
             size_t nb_part = (size_t)s->red_blocks;
-            if (s->use_tps && !s->tps_big.empty()) nb_part = std::max(nb_part, (size_t)((s->tps_big[0].nslabs + 127) / 128));
+            if (s->use_tps && !s->tps_big.empty()) nb_part = std::max(nb_part, (size_t)((s->tps_big[0].nslabs + 31) / 32));
             TRY(dev_alloc(s, &s->d_partials, nb_part * 4));
         }
         TRY(dev_alloc(s, &s->d_scal, (size_t)16));  // two result slots: undamped step / first damping trial
@@ -1059,9 +1065,10 @@ extern "C" int rst_b200_factor_local(rst_b200_solver *s) {
     CUDA_TRY(cudaMemsetAsync(s->d_flags, 0, sizeof(unsigned), s->stream));
     if (s->use_tps) {
         for (auto &lv : s->tps_big) {
-            const unsigned blocks = (unsigned)((lv.nslabs + 127) / 128);
-            if (lv.B == nullptr) tps_factor_kernel<2, TPS_S, true><<<blocks, 128, 0, s->stream>>>(lv, s->d_flags);
-            else tps_factor_kernel<2, TPS_S, false><<<blocks, 128, 0, s->stream>>>(lv, s->d_flags);
+            const int tb = tps_block();
+            const unsigned blocks = (unsigned)((lv.nslabs + tb - 1) / tb);
+            if (lv.B == nullptr) tps_factor_kernel<2, TPS_S, true><<<blocks, tb, 0, s->stream>>>(lv, s->d_flags);
+            else tps_factor_kernel<2, TPS_S, false><<<blocks, tb, 0, s->stream>>>(lv, s->d_flags);
             s->launches++;
         }
         const bool fused = fused_p2p(s);
@@ -1166,7 +1173,7 @@ extern "C" int rst_b200_solve_local_forward(rst_b200_solver *s) {
     if (!s->factored) return fail(RST_B200_ERR_NOT_FACTORIZED, "solve before factor");
     if (s->use_tps) {
         for (auto &lv : s->tps_big) {
-            tps_forward_kernel<2, TPS_S><<<(unsigned)((lv.nslabs + 127) / 128), 128, 0, s->stream>>>(lv);
+            tps_forward_kernel<2, TPS_S><<<(unsigned)((lv.nslabs + tps_block() - 1) / tps_block()), tps_block(), 0, s->stream>>>(lv);
             s->launches++;
         }
         if (s->world > 1 && !fused_p2p(s)) {  // otherwise the tail's forward sweep is fused with closure + backward sweep
@@ -1195,7 +1202,8 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
         s->launches++;
         for (int i = (int)s->tps_big.size() - 1; i >= 0; --i) {
             const TpsLevel &lv = s->tps_big[i];
-            const unsigned blocks = (unsigned)((lv.nslabs + 127) / 128);
+            const int tb = tps_block();
+            const unsigned blocks = (unsigned)((lv.nslabs + tb - 1) / tb);
             if (i == 0 && s->fuse_reduce_state >= 0) {  // level 0: damping reductions ride along with the sweep
                 TpsReduce R{};
                 R.Y = s->fuse_reduce_state ? s->Yt : s->Y;
@@ -1204,11 +1212,11 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
                 R.has_left = (s->rank == 0); R.has_right = (s->rank == s->world - 1);
                 R.n_own = (s->rank == s->world - 1) ? s->n + 1 : s->n;
                 R.partials = s->d_partials;
-                tps_backward_reduce_kernel<2, TPS_S><<<blocks, 128, 0, s->stream>>>(lv, R);
+                tps_backward_reduce_kernel<2, TPS_S><<<blocks, tb, 0, s->stream>>>(lv, R);
                 s->reduce_ready = (int)blocks;
                 s->reduce_ready_state = s->fuse_reduce_state;
             } else {
-                tps_backward_kernel<2, TPS_S><<<blocks, 128, 0, s->stream>>>(lv);
+                tps_backward_kernel<2, TPS_S><<<blocks, tb, 0, s->stream>>>(lv);
             }
             s->launches++;
         }
@@ -1236,7 +1244,8 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
         s->launches++;
         for (int i = (int)s->tps_big.size() - 1; i >= 0; --i) {
             const TpsLevel &lv = s->tps_big[i];
-            const unsigned blocks = (unsigned)((lv.nslabs + 127) / 128);
+            const int tb = tps_block();
+            const unsigned blocks = (unsigned)((lv.nslabs + tb - 1) / tb);
             if (i == 0 && s->fuse_reduce_state >= 0) {  // level 0: damping reductions ride along with the sweep
                 TpsReduce R{};
                 R.Y = s->fuse_reduce_state ? s->Yt : s->Y;
@@ -1245,11 +1254,11 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
                 R.has_left = (s->rank == 0); R.has_right = (s->rank == s->world - 1);
                 R.n_own = (s->rank == s->world - 1) ? s->n + 1 : s->n;
                 R.partials = s->d_partials;
-                tps_backward_reduce_kernel<2, TPS_S><<<blocks, 128, 0, s->stream>>>(lv, R);
+                tps_backward_reduce_kernel<2, TPS_S><<<blocks, tb, 0, s->stream>>>(lv, R);
                 s->reduce_ready = (int)blocks;
                 s->reduce_ready_state = s->fuse_reduce_state;
             } else {
-                tps_backward_kernel<2, TPS_S><<<blocks, 128, 0, s->stream>>>(lv);
+                tps_backward_kernel<2, TPS_S><<<blocks, tb, 0, s->stream>>>(lv);
             }
             s->launches++;
         }

@@ -470,6 +470,21 @@ __device__ void tps_top_solve(const double *C, const double *D, const double *g,
 template <int NV, int S>
 __global__ void __launch_bounds__(256) tps_tail_solve_kernel(TpsTail T, P2pIface I, unsigned long long seq, int phases,
                                                              unsigned *flags) {
+    // The tail runs right after the level-0..2 sweeps have streamed > 100 MB through the L2: its own factors (a few
+    // hundred KB) are gone by then and every slab step would pay a dependent DRAM round trip.  Pull them back in one burst.
+    if (phases & 5) {
+        for (int l = 0; l < T.nlevels; ++l) {
+            const TpsLevel &L = T.lv[l];
+            const size_t fac_bytes = (size_t)(S - 1) * TpsCfg<NV>::NE * L.nslabs * sizeof(double);
+            const char *pf = reinterpret_cast<const char *>(L.fac);
+            for (size_t off = (size_t)threadIdx.x * 128; off < fac_bytes; off += (size_t)blockDim.x * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + off));
+            const size_t bit_bytes = (size_t)(S - 1) * L.nslabs * sizeof(unsigned);
+            const char *pb = reinterpret_cast<const char *>(L.bits);
+            for (size_t off = (size_t)threadIdx.x * 128; off < bit_bytes; off += (size_t)blockDim.x * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + off));
+        }
+    }
     if (phases & 1) {
         for (int l = 0; l < T.nlevels; ++l) {
             const TpsLevel &L = T.lv[l];

@@ -61,6 +61,49 @@ __device__ __forceinline__ unsigned group_bits(unsigned ballot, int gw) {
     else return (ballot >> (gw * G)) & ((1u << G) - 1u);
 }
 
+// Packed factor layout of the lanes-per-slab kernels (per block row g):
+//   Lm  [k][rank]   only the rows that are updated at step k (not yet pivoted, not the pivot row) store a multiplier, compacted
+//                   by their rank among those rows: 2nv - k - 1 entries at offset k (2nv - 1) - k (k - 1) / 2
+//                   -> 1.5 nv^2 - nv/2 doubles instead of 2 nv^2
+//   UEF U part [c][k <= c]  upper triangle incl. diagonal at offset c (c + 1) / 2 + k; E, F full [c][k] behind it
+//                   -> 2.5 nv^2 + nv/2 doubles instead of 3 nv^2
+// 20 % less solve traffic than the dense layout (which the run-time-nv kernels of big.cuh keep, in the same buffers).
+template <int NV>
+struct AbdPack {
+    static constexpr int R2 = 2 * NV;
+    static constexpr int LM = NV * (R2 - 1) - NV * (NV - 1) / 2;
+    static constexpr int TRI = NV * (NV + 1) / 2;
+    static constexpr int UEF = TRI + 2 * NV * NV;
+    __host__ __device__ static constexpr int lm_off(int k) { return k * (R2 - 1) - k * (k - 1) / 2; }
+    __host__ __device__ static constexpr int u_off(int c) { return c * (c + 1) / 2; }
+};
+
+// factors of one block row from the register panel (all lanes of the warp must call: ballots inside)
+template <int NV, int G>
+__device__ __forceinline__ void abd_store_factors(const AbdLevel &L, int64_t g, int r, int gw, bool live, int pv,
+                                                  const double *M, const double *P, const double *Q) {
+    using Pk = AbdPack<NV>;
+    double *lm = L.Lm + g * (int64_t)Pk::LM;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const bool upd = live && (pv < 0 || pv > k);
+        const unsigned m = group_bits<G>(__ballot_sync(RST_FULL_MASK, upd), gw);
+        if (upd) st_cs(lm + Pk::lm_off(k) + rank_in(m, r), M[k]);
+    }
+    if (live) {
+        L.piv[g * Pk::R2 + r] = (int8_t)pv;
+        if (pv >= 0) {
+            double *u = L.UEF + g * (int64_t)Pk::UEF + pv;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                if (c >= pv) st_cs(u + Pk::u_off(c), M[c]);
+                st_cs(u + Pk::TRI + c * NV, P[c]);
+                st_cs(u + Pk::TRI + NV * NV + c * NV, Q[c]);
+            }
+        }
+    }
+}
+
 // arg-max of |v| over the lanes of a group that are still candidates; returns the group-relative lane.
 // Key = bits(|v|) with the low 5 mantissa bits replaced by (31 - r): ties resolve to the lowest row,
 // the comparison ignores the last 5 of 52 mantissa bits (irrelevant for stability).
@@ -157,22 +200,8 @@ __global__ void __launch_bounds__(128) abd_factor_kernel(AbdLevel L, unsigned *f
                 Q[c] = fma(-l, qp, Q[c]);
             }
         }
+        abd_store_factors<NV, G>(L, g, r, gw, active && row_ok, pv, M, P, Q);
         if (active) {
-            if (row_ok) {
-                double *lm = L.Lm + g * (int64_t)(NV * R2) + r;
-#pragma unroll
-                for (int k = 0; k < NV; ++k) st_cs(lm + k * R2, M[k]);
-                L.piv[g * R2 + r] = (int8_t)pv;
-                if (pv >= 0) {
-                    double *u = L.UEF + g * (int64_t)(3 * NV * NV) + pv;
-#pragma unroll
-                    for (int c = 0; c < NV; ++c) {
-                        st_cs(u + c * NV, M[c]);
-                        st_cs(u + (NV + c) * NV, P[c]);
-                        st_cs(u + (2 * NV + c) * NV, Q[c]);
-                    }
-                }
-            }
             carry = row_ok && pv < 0;
             if (carry) {
 #pragma unroll
@@ -195,6 +224,7 @@ __global__ void __launch_bounds__(128) abd_factor_kernel(AbdLevel L, unsigned *f
 // ------------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(128) abd_forward_kernel(AbdLevel L) {
+    using Pk = AbdPack<NV>;
     constexpr int R2 = 2 * NV;
     constexpr int G = next_pow2(R2);
     constexpr int GPW = 32 / G;
@@ -215,19 +245,26 @@ __global__ void __launch_bounds__(128) abd_forward_kernel(AbdLevel L) {
         const int64_t g = g0 + i;
         const bool is_free = row_ok && !carry;
         const unsigned fb = group_bits<G>(__ballot_sync(RST_FULL_MASK, is_free), gw);
-        if (L.prefetch && i + 1 < len && r * 128 < NV * R2 * 8)   // upper levels: one dependent DRAM round trip per block row
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(L.Lm + (g + 1) * (int64_t)(NV * R2)) + r * 128));
+        if (L.prefetch && i + 1 < len && r * 128 < Pk::LM * 8)   // upper levels: one dependent DRAM round trip per block row
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(L.Lm + (g + 1) * (int64_t)Pk::LM) + r * 128));
         int pv = -1;
         double lrow[NV];
-#pragma unroll
-        for (int k = 0; k < NV; ++k) lrow[k] = 0.0;
-        if (active && row_ok) {
+        const bool live = active && row_ok;
+        if (live) {
             if (is_free) w = L.r[g * NV + rank_in(fb, r)];
             pv = (int)L.piv[g * R2 + r];
-            const double *lm = L.Lm + g * (int64_t)(NV * R2) + r;
-#pragma unroll
-            for (int k = 0; k < NV; ++k) lrow[k] = ld_cs(lm + k * R2);
         }
+        {
+            const double *lm = L.Lm + g * (int64_t)Pk::LM;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {   // packed multipliers: rank among the rows updated at step k
+                const bool upd = live && (pv < 0 || pv > k);
+                const unsigned m = group_bits<G>(__ballot_sync(RST_FULL_MASK, upd), gw);
+                lrow[k] = upd ? ld_cs(lm + Pk::lm_off(k) + rank_in(m, r)) : 0.0;
+            }
+        }
+        // (deriving the ranks from the pivot ballots of the chain below saves 12 ballots, but ptxas then interleaves the
+        // loads with the chain and exposes one memory round trip per step: measured 1.56 ms vs 1.15 ms per C3 solve)
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const unsigned pb = group_bits<G>(__ballot_sync(RST_FULL_MASK, pv == k), gw);
@@ -249,6 +286,7 @@ __global__ void __launch_bounds__(128) abd_forward_kernel(AbdLevel L) {
 // ------------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(128) abd_backward_kernel(AbdLevel L) {
+    using Pk = AbdPack<NV>;
     constexpr int G = next_pow2(NV);
     constexpr int GPW = 32 / G;
     const int lane = threadIdx.x & 31;
@@ -281,19 +319,19 @@ __global__ void __launch_bounds__(128) abd_backward_kernel(AbdLevel L) {
 #pragma unroll
         for (int c = 0; c < NV; ++c) U[c] = 0.0;
         if (L.prefetch && slab_ok && i - 1 >= 1) {
-            const char *nx = reinterpret_cast<const char *>(L.UEF + (g - 1) * (int64_t)(3 * NV * NV));
-            for (int off = (lane & (G - 1)) * 128; off < 3 * NV * NV * 8; off += G * 128)
+            const char *nx = reinterpret_cast<const char *>(L.UEF + (g - 1) * (int64_t)Pk::UEF);
+            for (int off = (lane & (G - 1)) * 128; off < Pk::UEF * 8; off += G * 128)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + off));
         }
         if (active && k_ok) {
-            const double *u = L.UEF + g * (int64_t)(3 * NV * NV) + k;
+            const double *u = L.UEF + g * (int64_t)Pk::UEF + k;
             t = L.e[g * NV + k];
             double diag = 1.0;
 #pragma unroll
             for (int c = 0; c < NV; ++c) {
-                U[c] = ld_cs(u + c * NV);
-                t = fma(-ld_cs(u + (NV + c) * NV), Ys[c], t);
-                t = fma(-ld_cs(u + (2 * NV + c) * NV), Yn[c], t);
+                U[c] = (c >= k) ? ld_cs(u + Pk::u_off(c)) : 0.0;   // upper triangle only
+                t = fma(-ld_cs(u + Pk::TRI + c * NV), Ys[c], t);
+                t = fma(-ld_cs(u + Pk::TRI + NV * NV + c * NV), Yn[c], t);
                 diag = (c == k) ? U[c] : diag;
             }
             inv = 1.0 / diag;

@@ -141,22 +141,8 @@ __global__ void __launch_bounds__(128, 4) abd_factor3_kernel(AbdLevel L, unsigne
                 Q[c + 1] = fma(-l, q.y, Q[c + 1]);
             }
         }
+        abd_store_factors<NV, G>(L, g, r, gw, active && row_ok, pv, M, P, Q);
         if (active) {
-            if (row_ok) {
-                double *lm = L.Lm + g * (int64_t)(NV * R2) + r;
-#pragma unroll
-                for (int k = 0; k < NV; ++k) st_cs(lm + k * R2, M[k]);
-                L.piv[g * R2 + r] = (int8_t)pv;
-                if (pv >= 0) {
-                    double *u = L.UEF + g * (int64_t)(3 * NV * NV) + pv;
-#pragma unroll
-                    for (int c = 0; c < NV; ++c) {
-                        st_cs(u + c * NV, M[c]);
-                        st_cs(u + (NV + c) * NV, P[c]);
-                        st_cs(u + (2 * NV + c) * NV, Q[c]);
-                    }
-                }
-            }
             carry = row_ok && pv < 0;
             if (carry) {
 #pragma unroll

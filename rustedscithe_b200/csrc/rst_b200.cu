@@ -16,7 +16,6 @@
 #include <vector>
 
 #include "abd.cuh"
-#include "abd2.cuh"
 #include "abd3.cuh"
 #include "tps.cuh"
 #include "btd.cuh"
@@ -119,13 +118,12 @@ struct SolverVT {
                         const double *Bb, const double *bb, int nb, double *Z, unsigned *flags, cudaStream_t);
 };
 
-// kernel generation: "v1" = one panel row per lane + shuffle broadcast (abd.cuh), default "v2" = two rows per lane +
-// shared-memory broadcast (abd2.cuh).  Factor and forward kernels of one generation share the factor layout.
+// kernel generation: "v1" = one panel row per lane + shuffle broadcast (abd.cuh); default "v3" (abd3.cuh).  Both write
+// the packed factor layout of abd.cuh.  (Generation 2 -- two rows per lane -- was slower and is retired.)
 static int kernel_generation() {
     static int gen = [] {
         const char *e = std::getenv("RST_B200_KERNELS");
         if (e && std::strcmp(e, "v1") == 0) return 1;
-        if (e && std::strcmp(e, "v2") == 0) return 2;
         return 3;  // abd3.cuh: one row per lane, REDUX pivot search, shared-memory broadcast, reciprocal multipliers
     }();
     return gen;
@@ -139,15 +137,7 @@ struct SolverImpl {
         return (unsigned)((nslabs + per_block - 1) / per_block);
     }
     static void factor(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
-        if constexpr (NV % 2 == 0 && NV <= 12) {
-            if (kernel_generation() == 2) {
-                const unsigned blocks = grid_for(L.nslabs, NV);
-                if (ident_b) abd_factor2_kernel<NV, true><<<blocks, 128, 0, st>>>(L, flags);
-                else abd_factor2_kernel<NV, false><<<blocks, 128, 0, st>>>(L, flags);
-                return;
-            }
-            // REDUX with several sub-warp masks serialises per mask: generation 3 only where a slab spans >= 16 lanes
-        }
+        // REDUX with several sub-warp masks serialises per mask: generation 3 only where a slab spans >= 16 lanes
         if constexpr (NV % 2 == 0) {
             if (kernel_generation() >= 2 && NV >= 6) {
                 const unsigned blocks = grid_for(L.nslabs, 2 * NV);
@@ -161,12 +151,6 @@ struct SolverImpl {
         else abd_factor_kernel<NV, false><<<blocks, 128, 0, st>>>(L, flags);
     }
     static void forward(const AbdLevel &L, cudaStream_t st) {
-        if constexpr (NV % 2 == 0 && NV <= 12) {
-            if (kernel_generation() == 2) {
-                abd_forward2_kernel<NV><<<grid_for(L.nslabs, NV), 128, 0, st>>>(L);
-                return;
-            }
-        }
         abd_forward_kernel<NV><<<grid_for(L.nslabs, 2 * NV), 128, 0, st>>>(L);
     }
     static void backward(const AbdLevel &L, cudaStream_t st) {

@@ -37,7 +37,7 @@ struct AbdLevel {
     int64_t nslabs;    // ceil(n / S) = block rows of the next level
     int S;             // slab length (rows per slab)
     int nv;            // block size (used by the run-time-nv kernels of big.cuh)
-    int prefetch;      // != 0: small (latency-bound) level, the sweeps prefetch the next block row's factors into L2
+    int prefetch;      // != 0: the sweeps prefetch the next block row's factors into L2 while the current one is processed
     const double *A;   // [n][nv][nv] row-major
     const double *B;   // [n][nv][nv] or nullptr (identity)
     double *A_next;    // [nslabs][nv][nv]
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(128) abd_forward_kernel(AbdLevel L) {
         const int64_t g = g0 + i;
         const bool is_free = row_ok && !carry;
         const unsigned fb = group_bits<G>(__ballot_sync(RST_FULL_MASK, is_free), gw);
-        if (L.prefetch && i + 1 < len && r * 128 < Pk::LM * 8)   // upper levels: one dependent DRAM round trip per block row
+        if (L.prefetch && i + 1 < len && r * 128 < Pk::LM * 8)   // one line per lane; hides the per-block-row round trip
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(L.Lm + (g + 1) * (int64_t)Pk::LM) + r * 128));
         int pv = -1;
         double lrow[NV];

@@ -402,7 +402,7 @@ static int build_level(H *s, LevelBuf *lv, int64_t n, int S, const double *A, co
     k.n = n;
     k.S = S;
     k.nv = nv;
-    k.prefetch = ((n + S - 1) / S) <= 4096 ? 1 : 0;
+    k.prefetch = 1;   // measured at nv = 12, 1e6 rows: solve 1.15 -> 1.08 ms; distances 2 / 4 are not better
     k.nslabs = (n + S - 1) / S;
     k.A = A;
     k.B = B;

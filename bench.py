@@ -365,8 +365,10 @@ def main():
                      "solve": per_solve["linear_solves"] * phases["solve"]}
             dom = max(share, key=share.get)
             # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel(s) from the committed `ncu --set full`
-            # captures (profiles/r01_b_summary.md), per launch at 1e6 intervals; None where no capture exists
-            ncu_traffic = {("flame12", "solve"): 2.426e9 + 3.575e9, ("flame12", "factor"): 1.153e9 + 5.620e9}
+            # captures (profiles/r01_c_summary.md), per launch at 1e6 intervals (coupled64: measured at 2.5e5, scaled); None where no capture exists
+            ncu_traffic = {("flame12", "solve"): (1.773e9 + 0.062e9) + (3.060e9 + 0.087e9),     # forward + backward, level 0
+                           ("flame12", "factor"): 1.157e9 + 4.507e9,
+                           ("coupled64", "factor"): (8.22e9 + 40.20e9) * 4.0, ("coupled64", "solve"): (16.03e9 + 0.13e9 + 23.94e9 + 0.13e9) * 4.0}
             traffic = ncu_traffic.get((key, dom))
             if traffic is not None:
                 traffic *= n_local / 1e6

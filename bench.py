@@ -372,10 +372,18 @@ def main():
             traffic = ncu_traffic.get((key, dom))
             if traffic is not None:
                 traffic *= n_local / 1e6
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
-                        "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                        "share_of_step": share[dom] / ms_per_step,
-                        "note": "solve = forward + backward sweeps over all condensation levels"}
+            if key == "coupled64" and dom == "factor":
+                # wide blocks: 5 nv^3 FMA per block row against 160 KB of factor traffic (16 flop/B) -> FP64-pipe bound;
+                # peak = DFMA rate measured with tools/dfma_bench.cu on this pool's B200 (63.5 DFMA/clk/SM)
+                tflops = 2.0 * 5.0 * nv ** 3 * n_local / (phases["factor"] * 1e-3) / 1e12
+                roofline = {"kernel": "factor", "bound": "fp64", "achieved": tflops, "peak": 36.9, "unit": "TFLOP/s",
+                            "frac": tflops / 36.9, "traffic": traffic, "peak_source": "measured (tools/dfma_bench.cu)",
+                            "share_of_step": share[dom] / ms_per_step}
+            else:
+                roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+                            "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                            "share_of_step": share[dom] / ms_per_step,
+                            "note": "solve = forward + backward sweeps over all condensation levels"}
 
         # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the box's host cores -------------------
         cpu = None

@@ -34,6 +34,7 @@ def test_oracle_frozen_linear_bvp_is_exact(strategy, sp):
     ("damp1", 80, "every_m", (1,), 1e-8), ("damp1", 80, "Naive", (), 1e-9),
     ("combustion6", 200, "every_m", (2,), 1e-6), ("flame12", 150, "complex", (2, 1e-2, 0.5), 1e-6),
     ("flame12", 150, "at_low_speed", (0.5,), 1e-6), ("combustion6", 200, "at_high_morm", (1e-3,), 1e-6),
+    ("coupled64", 36, "every_m", (1,), 1e-6),          # wide-block kernels under the frozen loop
 ])
 def test_gpu_frozen_matches_oracle(key, n_steps, strategy, sp, tol):
     from rustedscithe_b200.solver import NRBVP
@@ -41,6 +42,11 @@ def test_gpu_frozen_matches_oracle(key, n_steps, strategy, sp, tol):
     bcs = LEFT_BCS if key == "linear2" else spec.bc_list()
     o = orc.OracleBVP(key, n_steps, bcs)
     y0 = _linear_guess(n_steps) if key == "linear2" else spec.guess(n_steps) * 0 + 0.6
+    if key == "coupled64":
+        # from 0.6 the undamped iterates of this case pass through a Jacobian with a pivot below the reference's 1e-14
+        # ZeroPivot threshold (lapack_style_banded.rs:398-403): the band LU gives up there, the condensation (other pivots,
+        # exact-zero test only) does not -- a documented difference, so the wide case starts from the catalogue guess
+        y0 = spec.guess(n_steps)
     ref = o.newton_frozen(y0, strategy, sp, tolerance=tol, max_iterations=40)
     bc_dict = {"y": [(0, 0.0)], "z": [(0, 1.0)]} if key == "linear2" else None
     g = NRBVP(key, y0, n_steps, boundary_conditions=bc_dict)

@@ -231,6 +231,26 @@ def test_newton_matches_oracle_iteration_counts_and_solution(key, n_steps):
     g.close()
 
 
+def test_wide_block_newton_trapezoid_matches_oracle():
+    """64-variable case with the trapezoid scheme (both Jacobian blocks A_j and B_j are assembled and condensed)."""
+    key, n_steps = "coupled64", 30
+    spec = problems.get(key)
+    o = _oracle(key, n_steps, "trapezoid")
+    lo, hi = spec.bounds_per_var()
+    ref = o.newton(spec.guess(n_steps), o.per_unknown(lo), o.per_unknown(hi), o.per_unknown(spec.rtol_per_var()),
+                   abs_tol=spec.abs_tol, max_iterations=spec.max_iterations, max_jac=spec.max_jac,
+                   max_damp_iter=spec.max_damp_iter, damp_factor=spec.damp_factor)
+    g = _gpu(key, n_steps, "trapezoid", guess=spec.guess(n_steps))
+    sol = g.try_solve()
+    st = g.get_statistics()
+    assert st["status"] == ref.status
+    assert (st["number of iterations"], st["number of solving linear systems"],
+            st["number of jacobians recalculations"]) == (ref.iterations, ref.linear_solves, ref.jac_recalcs)
+    if ref.status == 1:
+        assert np.max(np.abs(sol - ref.y) / np.maximum(1.0, np.abs(ref.y))) < TOL_SOL
+    g.close()
+
+
 def test_config_c1_closed_form():
     """examples/bvp_damped_aot_guide.rs:84-109 at N = 1000: max |y - x| < 5e-5."""
     spec = problems.get("linear2")

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -353,6 +354,11 @@ struct rst_b200_solver {
     unsigned long long *g_ext = nullptr;
     double *g_mesh_new = nullptr, *g_Y_new = nullptr;
     int64_t g_nodes_new = 0, g_added = -1, g_capacity = 0;
+    // CUDA graphs of the speculative damped step (undamped step + first damping trial + scalar read-back), one per parity of
+    // the Y / Y_trial buffers (accept_trial swaps them); single GPU only (the NVLink exchange carries a sequence number)
+    std::map<const double *, cudaGraphExec_t> step_graphs;
+    int64_t step_graph_launches = 0;
+    int spec_steps_seen = 0;
 };
 
 // nv == 2 path with mapped peers: the interface exchange + solve is fused into the single-CTA tail kernels
@@ -687,6 +693,7 @@ extern "C" void rst_b200_destroy(rst_b200_solver *s) {
     if (g_bound == s) g_bound = nullptr;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    for (auto &kv : s->step_graphs) cudaGraphExecDestroy(kv.second);
     for (void *p : s->peer_mapped) cudaIpcCloseMemHandle(p);
     for (void *p : s->owned) cudaFree(p);
     if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -1412,18 +1419,61 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
     // on the device, so undamped step + first trial are enqueued back to back and the host synchronises ONCE.
     const bool speculative = (s->world == 1 || s->p2p_enabled) && o->max_damp_iter > 0;
     s->scal_slot = 0;
-    TRY(newton_step(s, 0, st));
+    // The speculative sequence is ~25-45 launches with fixed arguments: small meshes are launch bound, so it is captured
+    // into a CUDA graph (per Y / Y_trial parity) the second time it runs and replayed with one launch afterwards.
+    static const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;
+    const bool graphable = speculative && s->world == 1 && graphs_on;
+    bool replayed = false;
+    if (graphable) {
+        auto it = s->step_graphs.find(s->Y);
+        if (it != s->step_graphs.end()) {
+            CUDA_TRY(cudaGraphLaunch(it->second, s->stream));
+            s->launches += s->step_graph_launches;
+            st->linear_solves += 2;
+            s->reduce_ready = 0;
+            s->fuse_reduce_state = -1;
+            replayed = true;
+        }
+    }
+    if (!replayed) {
+        const bool capture = graphable && s->spec_steps_seen >= 1;
+        const int64_t launches0 = s->launches;
+        if (capture) CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = [&]() -> int {
+            TRY(newton_step(s, 0, st));
+            if (!speculative) return RST_B200_OK;
+            TRY(rst_b200_reduce_local(s, 0));
+            set_solution_buffer(s, s->dY1);
+            const int64_t total = (s->n + 1) * (int64_t)s->nv;
+            newton_trial_dev_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY, s->Yt, s->d_scal, total);
+            s->launches++;
+            s->scal_slot = 1;
+            TRY(newton_step(s, 1, st));
+            TRY(rst_b200_reduce_local(s, 1));
+            s->scal_slot = 0;
+            CUDA_TRY(cudaMemcpyAsync(s->h_scal, s->d_scal, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+            return RST_B200_OK;
+        }();
+        if (capture) {
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+            if (rc != RST_B200_OK || e != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc != RST_B200_OK ? rc : fail(RST_B200_ERR_CUDA, std::string("graph capture of the damped step: ") + cudaGetErrorString(e));
+            }
+            cudaGraphExec_t exec = nullptr;
+            const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ei != cudaSuccess) return fail(RST_B200_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei));
+            s->step_graphs[s->Y] = exec;
+            s->step_graph_launches = s->launches - launches0;
+            CUDA_TRY(cudaGraphLaunch(exec, s->stream));   // capture records, it does not run
+        } else if (rc != RST_B200_OK) {
+            return rc;
+        }
+        if (speculative) s->spec_steps_seen++;
+    }
     if (speculative) {
-        TRY(rst_b200_reduce_local(s, 0));
-        set_solution_buffer(s, s->dY1);
-        const int64_t total = (s->n + 1) * (int64_t)s->nv;
-        newton_trial_dev_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY, s->Yt, s->d_scal, total);
-        s->launches++;
-        s->scal_slot = 1;
-        TRY(newton_step(s, 1, st));
-        TRY(rst_b200_reduce_local(s, 1));
-        s->scal_slot = 0;
-        CUDA_TRY(cudaMemcpyAsync(s->h_scal, s->d_scal, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         unpack_scalars(s->h_scal, &sc);
         unpack_scalars(s->h_scal + 8, &sc1);

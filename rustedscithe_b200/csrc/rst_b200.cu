@@ -359,6 +359,9 @@ struct rst_b200_solver {
     std::map<const double *, cudaGraphExec_t> step_graphs;
     int64_t step_graph_launches = 0;
     int spec_steps_seen = 0;
+    std::map<const double *, cudaGraphExec_t> jac_graphs;   // Jacobian assembly + factorisation of every level
+    int64_t jac_graph_launches = 0;
+    int jac_seen = 0;
 };
 
 // nv == 2 path with mapped peers: the interface exchange + solve is fused into the single-CTA tail kernels
@@ -694,6 +697,7 @@ extern "C" void rst_b200_destroy(rst_b200_solver *s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto &kv : s->step_graphs) cudaGraphExecDestroy(kv.second);
+    for (auto &kv : s->jac_graphs) cudaGraphExecDestroy(kv.second);
     for (void *p : s->peer_mapped) cudaIpcCloseMemHandle(p);
     for (void *p : s->owned) cudaFree(p);
     if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -1396,8 +1400,45 @@ static int newton_step(rst_b200_solver *s, int which, rst_b200_newton_stats *st)
 }
 
 static int recalc_jacobian(rst_b200_solver *s, rst_b200_newton_stats *st) {
-    TRY(rst_b200_eval_jacobian(s, 0));
-    TRY(rst_b200_factor(s));
+    static const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;
+    const bool graphable = s->world == 1 && graphs_on;   // fixed launch sequence with fixed arguments (per state buffer)
+    if (graphable) {
+        auto it = s->jac_graphs.find(s->Y);
+        if (it != s->jac_graphs.end()) {
+            CUDA_TRY(cudaGraphLaunch(it->second, s->stream));
+            s->launches += s->jac_graph_launches;
+            s->have_jac = s->factored = true;
+            st->jac_recalcs++;
+            st->factorizations++;
+            return RST_B200_OK;
+        }
+    }
+    const bool capture = graphable && s->jac_seen >= 1;
+    const int64_t launches0 = s->launches;
+    if (capture) CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = [&]() -> int {
+        TRY(rst_b200_eval_jacobian(s, 0));
+        TRY(rst_b200_factor(s));
+        return RST_B200_OK;
+    }();
+    if (capture) {
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+        if (rc != RST_B200_OK || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc != RST_B200_OK ? rc : fail(RST_B200_ERR_CUDA, std::string("graph capture of the Jacobian refresh: ") + cudaGetErrorString(e));
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) return fail(RST_B200_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei));
+        s->jac_graphs[s->Y] = exec;
+        s->jac_graph_launches = s->launches - launches0;
+        CUDA_TRY(cudaGraphLaunch(exec, s->stream));
+    } else if (rc != RST_B200_OK) {
+        return rc;
+    }
+    s->jac_seen++;
     st->jac_recalcs++;
     st->factorizations++;
     return RST_B200_OK;

@@ -21,6 +21,9 @@ constexpr int P2P_MAX_WORLD = 16;
 
 struct P2pPeers {
     double *mailbox[P2P_MAX_WORLD];  // peer mailboxes (own entry = local pointer)
+    // exchange sequence number, kept on the DEVICE (every rank runs the same exchanges in stream order, so the local
+    // counters agree): kernel arguments stay constant from launch to launch and the sequences can be replayed as CUDA graphs
+    unsigned long long *seq_dev;
 };
 
 // mailbox layout: payload[2][world][pay] doubles, then flags[2][world] unsigned long long
@@ -40,10 +43,15 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void p2p_allgather_block(const P2pPeers &peers, const double *send, int count, double *recv,
                                                     int my_rank, int world, int pay, unsigned long long seq,
                                                     unsigned *flags) {
+    (void)seq;   // legacy argument: the sequence number lives in peers.seq_dev
+    __shared__ unsigned long long seq_sh;
+    __syncthreads();  // `send` may have been produced by other threads of this CTA
+    if (threadIdx.x == 0) seq_sh = *peers.seq_dev + 1ull;
+    __syncthreads();
+    seq = seq_sh;
     const int parity = (int)(seq & 1ull);
     const size_t slot = ((size_t)parity * world + my_rank) * pay;
     const size_t flag_base = (size_t)2 * world * pay;
-    __syncthreads();  // `send` may have been produced by other threads of this CTA
     for (int p = 0; p < world; ++p) {
         double *dst = peers.mailbox[p] + slot;
         for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = send[i];
@@ -70,6 +78,7 @@ __device__ __forceinline__ void p2p_allgather_block(const P2pPeers &peers, const
         const int p = idx / count, i = idx - p * count;
         recv[idx] = __ldcg(mine + (size_t)p * pay + i);
     }
+    if (threadIdx.x == 0) *peers.seq_dev = seq;
     __syncthreads();
 }
 

@@ -355,7 +355,8 @@ struct rst_b200_solver {
     double *g_mesh_new = nullptr, *g_Y_new = nullptr;
     int64_t g_nodes_new = 0, g_added = -1, g_capacity = 0;
     // CUDA graphs of the speculative damped step (undamped step + first damping trial + scalar read-back), one per parity of
-    // the Y / Y_trial buffers (accept_trial swaps them); single GPU only (the NVLink exchange carries a sequence number)
+    // the Y / Y_trial buffers (accept_trial swaps them); multi-GPU with the NVLink mailboxes too (the exchange sequence
+    // number lives on the device)
     std::map<const double *, cudaGraphExec_t> step_graphs;
     int64_t step_graph_launches = 0;
     int spec_steps_seen = 0;
@@ -1140,6 +1141,12 @@ extern "C" int rst_b200_p2p_open(rst_b200_solver *s, const void *handles, size_t
         s->peer_mapped.push_back(ptr);
         s->peers.mailbox[p] = (double *)ptr;
     }
+    {   // device-side exchange counter
+        unsigned long long *d_seq = nullptr;
+        TRY(dev_alloc(s, &d_seq, (size_t)1));
+        CUDA_TRY(cudaMemset(d_seq, 0, sizeof(unsigned long long)));
+        s->peers.seq_dev = d_seq;
+    }
     s->p2p_enabled = true;
     P2pIface &I = s->iface;
     I.peers = s->peers;
@@ -1401,7 +1408,7 @@ static int newton_step(rst_b200_solver *s, int which, rst_b200_newton_stats *st)
 
 static int recalc_jacobian(rst_b200_solver *s, rst_b200_newton_stats *st) {
     static const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;
-    const bool graphable = s->world == 1 && graphs_on;   // fixed launch sequence with fixed arguments (per state buffer)
+    const bool graphable = (s->world == 1 || s->p2p_enabled) && graphs_on;   // fixed launch sequence, fixed arguments (per state buffer)
     if (graphable) {
         auto it = s->jac_graphs.find(s->Y);
         if (it != s->jac_graphs.end()) {
@@ -1463,7 +1470,7 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
     // The speculative sequence is ~25-45 launches with fixed arguments: small meshes are launch bound, so it is captured
     // into a CUDA graph (per Y / Y_trial parity) the second time it runs and replayed with one launch afterwards.
     static const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;
-    const bool graphable = speculative && s->world == 1 && graphs_on;
+    const bool graphable = speculative && (s->world == 1 || s->p2p_enabled) && graphs_on;
     bool replayed = false;
     if (graphable) {
         auto it = s->step_graphs.find(s->Y);

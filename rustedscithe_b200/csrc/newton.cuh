@@ -189,6 +189,22 @@ __global__ void __launch_bounds__(256) newton_reduce_final_kernel(const double *
     }
 }
 
+// last node of the damped-step sequence: both scalar sets go straight into mapped pinned host memory, followed by a ticket
+// the host spins on (a stream synchronise costs ~10 us of turnaround per Newton iteration; the ticket counter lives on the
+// device so the launch is graph-replayable)
+__global__ void __launch_bounds__(32) publish_scalars_kernel(const double *__restrict__ d_scal, double *h_scal,
+                                                             unsigned long long *d_ticket, volatile unsigned long long *h_ticket) {
+    if (threadIdx.x < 16) h_scal[threadIdx.x] = d_scal[threadIdx.x];
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        const unsigned long long t = *d_ticket + 1ull;
+        *d_ticket = t;
+        *h_ticket = t;
+        __threadfence_system();
+    }
+}
+
 // y_trial = y - lambda * step   (NR_Damp_solver_damped.rs:1934-1935: mul_float, then subtraction)
 __global__ void __launch_bounds__(256) newton_trial_kernel(const double *__restrict__ Y, const double *__restrict__ dY,
                                                            double *__restrict__ Yt, double lambda, int64_t total) {

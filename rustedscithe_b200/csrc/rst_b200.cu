@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <string>
 #include <vector>
@@ -317,7 +318,9 @@ struct rst_b200_solver {
     // reductions
     int red_blocks = 0;
     double *d_partials = nullptr, *d_scal = nullptr, *d_gscal = nullptr;
-    double *h_scal = nullptr;  // pinned
+    double *h_scal = nullptr;  // pinned (mapped): [0..15] two scalar sets, [16] ticket written by publish_scalars_kernel
+    unsigned long long *d_ticket = nullptr;
+    unsigned long long ticket_expected = 0;
     unsigned *d_flags = nullptr;
     // value-stream map for the legacy AOT ABI
     std::vector<int64_t> st_rows, st_cols;
@@ -679,7 +682,10 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
         }
         TRY(dev_alloc(s, &s->d_scal, (size_t)16));  // two result slots: undamped step / first damping trial
         TRY(dev_alloc(s, &s->d_gscal, (size_t)8 * world));
-        CUDA_TRY(cudaMallocHost((void **)&s->h_scal, 16 * sizeof(double)));
+        CUDA_TRY(cudaMallocHost((void **)&s->h_scal, 32 * sizeof(double)));
+        std::memset(s->h_scal, 0, 32 * sizeof(double));
+        TRY(dev_alloc(s, &s->d_ticket, (size_t)1));
+        CUDA_TRY(cudaMemsetAsync(s->d_ticket, 0, sizeof(unsigned long long), s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         return RST_B200_OK;
     };
@@ -1499,7 +1505,9 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
             TRY(newton_step(s, 1, st));
             TRY(rst_b200_reduce_local(s, 1));
             s->scal_slot = 0;
-            CUDA_TRY(cudaMemcpyAsync(s->h_scal, s->d_scal, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+            publish_scalars_kernel<<<1, 32, 0, s->stream>>>(s->d_scal, s->h_scal, s->d_ticket,
+                                                          reinterpret_cast<volatile unsigned long long *>(s->h_scal + 16));
+            s->launches++;
             return RST_B200_OK;
         }();
         if (capture) {
@@ -1522,7 +1530,18 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
         if (speculative) s->spec_steps_seen++;
     }
     if (speculative) {
-        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        // wait for the ticket of this sequence instead of synchronising the stream
+        const unsigned long long want = ++s->ticket_expected;
+        volatile unsigned long long *tk = reinterpret_cast<volatile unsigned long long *>(s->h_scal + 16);
+        for (unsigned spin = 0; *tk < want; ++spin) {
+            if ((spin & 0x3fff) == 0x3fff) {   // every ~16k polls: has the stream died?
+                const cudaError_t q = cudaStreamQuery(s->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady)
+                    return fail(RST_B200_ERR_CUDA, std::string("damped step: ") + cudaGetErrorString(q));
+                if (q == cudaSuccess && *tk < want) return fail(RST_B200_ERR_CUDA, "damped step finished without publishing its scalars");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
         unpack_scalars(s->h_scal, &sc);
         unpack_scalars(s->h_scal + 8, &sc1);
     } else {

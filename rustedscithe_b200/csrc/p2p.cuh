@@ -5,10 +5,10 @@
 // 8 damping scalars per trial.  Through NCCL + a host callback each of them costs ~25 us of launch/host latency,
 // which is a quarter of a 1 ms Newton solve at C2.  Here every rank owns a "mailbox" in its HBM that its peers map
 // through CUDA IPC; the gather is ONE small kernel per rank on the solver's own stream:
-//   1. store my payload into slot [parity][my_rank] of every peer's mailbox (peer stores travel over NVLink),
-//   2. __threadfence_system(), then release-store the sequence number into the peers' flag words,
-//   3. acquire-spin on my own flag words until every peer's sequence number has arrived,
-//   4. copy my mailbox (L1 bypassed) into the local gather buffer.
+//   1. store my payload into slot [parity][my_rank] of every peer's mailbox (peer stores travel over NVLink) as 16-byte
+//      (value, sequence number) pairs -- one aligned vector store each, so a value and its tag arrive together and no
+//      fence + separate flag round trip is needed (the low-latency "LL" protocol of collective libraries),
+//   2. spin on every pair of my own mailbox until its tag equals the sequence number, keep the value.
 // One process per GPU, so the kernels of different ranks always run concurrently (each on its own device); slots are
 // double-buffered by the parity of the sequence number: a rank cannot run two gathers ahead of a peer because it
 // waits for that peer's flag of the gather in between.
@@ -26,8 +26,17 @@ struct P2pPeers {
     unsigned long long *seq_dev;
 };
 
-// mailbox layout: payload[2][world][pay] doubles, then flags[2][world] unsigned long long
-__host__ __device__ inline size_t p2p_mailbox_doubles(int world, int pay) { return (size_t)2 * world * pay + (size_t)2 * world; }
+// mailbox layout: pairs[2][world][pay] of (value, tag) = 2 doubles each
+__host__ __device__ inline size_t p2p_mailbox_doubles(int world, int pay) { return (size_t)2 * 2 * world * pay; }
+
+__device__ __forceinline__ void st_pair_sys(double *p, double v, unsigned long long tag) {
+    asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
+}
+__device__ __forceinline__ void ld_pair_sys(const double *p, double &v, unsigned long long &tag) {
+    long long a;
+    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(tag) : "l"(p) : "memory");
+    v = __longlong_as_double(a);
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -50,34 +59,29 @@ __device__ __forceinline__ void p2p_allgather_block(const P2pPeers &peers, const
     __syncthreads();
     seq = seq_sh;
     const int parity = (int)(seq & 1ull);
-    const size_t slot = ((size_t)parity * world + my_rank) * pay;
-    const size_t flag_base = (size_t)2 * world * pay;
+    const size_t slot = ((size_t)parity * world + my_rank) * pay * 2;          // in doubles: pairs of (value, tag)
     for (int p = 0; p < world; ++p) {
         double *dst = peers.mailbox[p] + slot;
-        for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = send[i];
+        for (int i = threadIdx.x; i < count; i += blockDim.x) st_pair_sys(dst + 2 * i, send[i], seq);
     }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < world) {
-        unsigned long long *pf = reinterpret_cast<unsigned long long *>(peers.mailbox[threadIdx.x] + flag_base) +
-                                 (size_t)parity * world + my_rank;
-        st_release_sys(pf, seq);
-        const unsigned long long *mf = reinterpret_cast<const unsigned long long *>(peers.mailbox[my_rank] + flag_base) +
-                                       (size_t)parity * world + threadIdx.x;
+    const double *mine = peers.mailbox[my_rank] + (size_t)parity * world * pay * 2;
+    for (int idx = threadIdx.x; idx < world * count; idx += blockDim.x) {
+        const int p = idx / count, i = idx - p * count;
+        const double *src = mine + ((size_t)p * pay + i) * 2;
+        double v;
+        unsigned long long tag;
         const long long t0 = clock64();
-        while (ld_acquire_sys(mf) < seq) {
+        for (;;) {
+            ld_pair_sys(src, v, tag);
+            if (tag == seq) break;
             if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer never arrived
                 atomicOr(flags, RST_FLAG_PEER_TIMEOUT);
                 break;
             }
         }
+        recv[idx] = v;
     }
     __syncthreads();
-    const double *mine = peers.mailbox[my_rank] + (size_t)parity * world * pay;
-    for (int idx = threadIdx.x; idx < world * count; idx += blockDim.x) {
-        const int p = idx / count, i = idx - p * count;
-        recv[idx] = __ldcg(mine + (size_t)p * pay + i);
-    }
     if (threadIdx.x == 0) *peers.seq_dev = seq;
     __syncthreads();
 }

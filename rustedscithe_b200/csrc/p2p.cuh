@@ -38,15 +38,6 @@ __device__ __forceinline__ void ld_pair_sys(const double *p, double &v, unsigned
     v = __longlong_as_double(a);
 }
 
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // The gather as a block-wide device function (every thread of ONE CTA calls it): used stand-alone below and fused into
 // the single-CTA tail / reduction kernels so a multi-GPU solve needs no extra launches.
 __device__ __forceinline__ void p2p_allgather_block(const P2pPeers &peers, const double *send, int count, double *recv,

@@ -367,6 +367,8 @@ struct rst_b200_solver {
     std::map<const double *, cudaGraphExec_t> jac_graphs;   // Jacobian assembly + factorisation of every level
     int64_t jac_graph_launches = 0;
     int jac_seen = 0;
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0; };
+    std::map<uintptr_t, GraphEntry> frozen_graphs;          // frozen-Jacobian iteration, key = Y buffer | recalc flag
 };
 
 // nv == 2 path with mapped peers: the interface exchange + solve is fused into the single-CTA tail kernels
@@ -706,6 +708,7 @@ extern "C" void rst_b200_destroy(rst_b200_solver *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto &kv : s->step_graphs) cudaGraphExecDestroy(kv.second);
     for (auto &kv : s->jac_graphs) cudaGraphExecDestroy(kv.second);
+    for (auto &kv : s->frozen_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (void *p : s->peer_mapped) cudaIpcCloseMemHandle(p);
     for (void *p : s->owned) cudaFree(p);
     if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -1413,6 +1416,38 @@ static int newton_step(rst_b200_solver *s, int which, rst_b200_newton_stats *st)
     return RST_B200_OK;
 }
 
+// Run `body` (enqueue-only work on s->stream with launch-invariant arguments) through a CUDA graph cache: the first time a
+// key is seen the body runs directly, the second time it is captured, instantiated and launched, afterwards replayed.
+template <class Body>
+static int run_graphed(rst_b200_solver *s, std::map<uintptr_t, rst_b200_solver::GraphEntry> &cache, uintptr_t key, bool enabled,
+                       bool *replayed, Body body) {
+    *replayed = false;
+    if (!enabled) return body();
+    auto &ge = cache[key];
+    if (ge.exec) {
+        CUDA_TRY(cudaGraphLaunch(ge.exec, s->stream));
+        s->launches += ge.launches;
+        *replayed = true;
+        return RST_B200_OK;
+    }
+    if (ge.seen++ < 1) return body();
+    const int64_t launches0 = s->launches;
+    CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+    if (rc != RST_B200_OK || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc != RST_B200_OK ? rc : fail(RST_B200_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) { ge.exec = nullptr; return fail(RST_B200_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei)); }
+    ge.launches = s->launches - launches0;
+    CUDA_TRY(cudaGraphLaunch(ge.exec, s->stream));   // capture records, it does not run
+    return RST_B200_OK;
+}
+
 static int recalc_jacobian(rst_b200_solver *s, rst_b200_newton_stats *st) {
     static const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;
     const bool graphable = (s->world == 1 || s->p2p_enabled) && graphs_on;   // fixed launch sequence, fixed arguments (per state buffer)
@@ -1656,29 +1691,70 @@ extern "C" int rst_b200_newton_frozen(rst_b200_solver *s, const rst_b200_frozen_
     if (!s || !o || !st) return fail(RST_B200_ERR_INVALID, "null argument");
     if (o->strategy < 0 || o->strategy > RST_B200_FROZEN_COMPLEX) return fail(RST_B200_ERR_INVALID, "unknown strategy");
     std::memset(st, 0, sizeof(*st));
-    cudaEventRecord(s->ev[0], s->stream);
+    const auto t_begin = std::chrono::steady_clock::now();
     bool jac_recalc = true, have_jac = false;
     int m = 0, it = 0, status = 0;
     double error_old = 0.0;
     rst_b200_scalars sc{};
+    // device-only exchange (1 GPU or NVLink mailboxes): one iteration is an enqueue-only sequence with launch-invariant
+    // arguments -> CUDA graph per (state buffer, refresh-or-not), scalars published to mapped host memory with a ticket
+    static const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;
+    const bool fast = s->world == 1 || s->p2p_enabled;
     while (it < o->max_iterations) {
         st->iterations++;
-        if (jac_recalc) {  // F(y) and J(y) in one fused pass, then the (cached) factorisation
-            TRY(rst_b200_eval_jacobian(s, 0));
-            TRY(rst_b200_factor(s));
+        if (jac_recalc) {
             have_jac = true;
             m = 0;
             st->jac_recalcs++;
             st->factorizations++;
         } else {
             m += 1;
-            TRY(rst_b200_eval_residual(s, 0));
         }
-        TRY(rst_b200_solve(s));
         st->linear_solves++;
-        TRY(rst_b200_reduce(s, 0, &sc));
+        if (fast) {
+            bool replayed = false;
+            const bool refresh = jac_recalc;
+            TRY(run_graphed(s, s->frozen_graphs, (uintptr_t)s->Y | (refresh ? 1u : 0u), graphs_on, &replayed, [&]() -> int {
+                if (refresh) {  // F(y) and J(y) in one fused pass, then the (cached) factorisation
+                    TRY(rst_b200_eval_jacobian(s, 0));
+                    TRY(rst_b200_factor(s));
+                } else {
+                    TRY(rst_b200_eval_residual(s, 0));
+                }
+                TRY(rst_b200_solve(s));
+                s->scal_slot = 0;
+                TRY(rst_b200_reduce_local(s, 0));
+                TRY(rst_b200_make_trial(s, 1.0));  // y_new = y - delta
+                publish_scalars_kernel<<<1, 32, 0, s->stream>>>(s->d_scal, s->h_scal, s->d_ticket,
+                                                              reinterpret_cast<volatile unsigned long long *>(s->h_scal + 16));
+                s->launches++;
+                return RST_B200_OK;
+            }));
+            if (replayed && refresh) s->have_jac = s->factored = true;
+            const unsigned long long want = ++s->ticket_expected;
+            volatile unsigned long long *tk = reinterpret_cast<volatile unsigned long long *>(s->h_scal + 16);
+            for (unsigned spin = 0; *tk < want; ++spin) {
+                if ((spin & 0x3fff) == 0x3fff) {
+                    const cudaError_t q = cudaStreamQuery(s->stream);
+                    if (q != cudaSuccess && q != cudaErrorNotReady)
+                        return fail(RST_B200_ERR_CUDA, std::string("frozen iteration: ") + cudaGetErrorString(q));
+                    if (q == cudaSuccess && *tk < want) return fail(RST_B200_ERR_CUDA, "frozen iteration finished without publishing its scalars");
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            unpack_scalars(s->h_scal, &sc);
+        } else {
+            if (jac_recalc) {
+                TRY(rst_b200_eval_jacobian(s, 0));
+                TRY(rst_b200_factor(s));
+            } else {
+                TRY(rst_b200_eval_residual(s, 0));
+            }
+            TRY(rst_b200_solve(s));
+            TRY(rst_b200_reduce(s, 0, &sc));
+        }
         TRY(check_scalars(sc));
-        TRY(rst_b200_make_trial(s, 1.0));  // y_new = y - delta
+        if (!fast) TRY(rst_b200_make_trial(s, 1.0));  // y_new = y - delta
         TRY(rst_b200_accept_trial(s));
         const double error = std::sqrt(sc.sumsq_step);  // ||y_new - y||
         jac_recalc = frozen_recalc(o, have_jac, m, error, error_old);
@@ -1687,11 +1763,8 @@ extern "C" int rst_b200_newton_frozen(rst_b200_solver *s, const rst_b200_frozen_
         if (error < o->tolerance) { status = 1; break; }
         it += 1;
     }
-    cudaEventRecord(s->ev[1], s->stream);
-    cudaEventSynchronize(s->ev[1]);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]);
-    st->ms_total = ms;
+    if (!fast) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    st->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     st->status = status;
     return RST_B200_OK;
 }

@@ -361,14 +361,10 @@ struct rst_b200_solver {
     // CUDA graphs of the speculative damped step (undamped step + first damping trial + scalar read-back), one per parity of
     // the Y / Y_trial buffers (accept_trial swaps them); multi-GPU with the NVLink mailboxes too (the exchange sequence
     // number lives on the device)
-    std::map<const double *, cudaGraphExec_t> step_graphs;
-    int64_t step_graph_launches = 0;
-    int spec_steps_seen = 0;
-    std::map<const double *, cudaGraphExec_t> jac_graphs;   // Jacobian assembly + factorisation of every level
-    int64_t jac_graph_launches = 0;
-    int jac_seen = 0;
     struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0; };
-    std::map<uintptr_t, GraphEntry> frozen_graphs;          // frozen-Jacobian iteration, key = Y buffer | recalc flag
+    std::map<uintptr_t, GraphEntry> step_graphs;            // speculative damped step, key = Y buffer
+    std::map<uintptr_t, GraphEntry> jac_graphs;             // Jacobian assembly + factorisation of every level
+    std::map<uintptr_t, GraphEntry> frozen_graphs;          // frozen-Jacobian iteration, key = Y buffer | refresh flag
 };
 
 // nv == 2 path with mapped peers: the interface exchange + solve is fused into the single-CTA tail kernels
@@ -706,9 +702,9 @@ extern "C" void rst_b200_destroy(rst_b200_solver *s) {
     if (g_bound == s) g_bound = nullptr;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    for (auto &kv : s->step_graphs) cudaGraphExecDestroy(kv.second);
-    for (auto &kv : s->jac_graphs) cudaGraphExecDestroy(kv.second);
-    for (auto &kv : s->frozen_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    for (auto *cache : {&s->step_graphs, &s->jac_graphs, &s->frozen_graphs})
+        for (auto &kv : *cache)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (void *p : s->peer_mapped) cudaIpcCloseMemHandle(p);
     for (void *p : s->owned) cudaFree(p);
     if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -1450,44 +1446,13 @@ static int run_graphed(rst_b200_solver *s, std::map<uintptr_t, rst_b200_solver::
 
 static int recalc_jacobian(rst_b200_solver *s, rst_b200_newton_stats *st) {
     static const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;
-    const bool graphable = (s->world == 1 || s->p2p_enabled) && graphs_on;   // fixed launch sequence, fixed arguments (per state buffer)
-    if (graphable) {
-        auto it = s->jac_graphs.find(s->Y);
-        if (it != s->jac_graphs.end()) {
-            CUDA_TRY(cudaGraphLaunch(it->second, s->stream));
-            s->launches += s->jac_graph_launches;
-            s->have_jac = s->factored = true;
-            st->jac_recalcs++;
-            st->factorizations++;
-            return RST_B200_OK;
-        }
-    }
-    const bool capture = graphable && s->jac_seen >= 1;
-    const int64_t launches0 = s->launches;
-    if (capture) CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = [&]() -> int {
+    bool replayed = false;   // fixed launch sequence with fixed arguments per state buffer
+    TRY(run_graphed(s, s->jac_graphs, (uintptr_t)s->Y, (s->world == 1 || s->p2p_enabled) && graphs_on, &replayed, [&]() -> int {
         TRY(rst_b200_eval_jacobian(s, 0));
         TRY(rst_b200_factor(s));
         return RST_B200_OK;
-    }();
-    if (capture) {
-        cudaGraph_t graph = nullptr;
-        const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
-        if (rc != RST_B200_OK || e != cudaSuccess || !graph) {
-            if (graph) cudaGraphDestroy(graph);
-            return rc != RST_B200_OK ? rc : fail(RST_B200_ERR_CUDA, std::string("graph capture of the Jacobian refresh: ") + cudaGetErrorString(e));
-        }
-        cudaGraphExec_t exec = nullptr;
-        const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ei != cudaSuccess) return fail(RST_B200_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei));
-        s->jac_graphs[s->Y] = exec;
-        s->jac_graph_launches = s->launches - launches0;
-        CUDA_TRY(cudaGraphLaunch(exec, s->stream));
-    } else if (rc != RST_B200_OK) {
-        return rc;
-    }
-    s->jac_seen++;
+    }));
+    if (replayed) s->have_jac = s->factored = true;
     st->jac_recalcs++;
     st->factorizations++;
     return RST_B200_OK;
@@ -1512,24 +1477,9 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
     // The speculative sequence is ~25-45 launches with fixed arguments: small meshes are launch bound, so it is captured
     // into a CUDA graph (per Y / Y_trial parity) the second time it runs and replayed with one launch afterwards.
     static const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;
-    const bool graphable = speculative && (s->world == 1 || s->p2p_enabled) && graphs_on;
-    bool replayed = false;
-    if (graphable) {
-        auto it = s->step_graphs.find(s->Y);
-        if (it != s->step_graphs.end()) {
-            CUDA_TRY(cudaGraphLaunch(it->second, s->stream));
-            s->launches += s->step_graph_launches;
-            st->linear_solves += 2;
-            s->reduce_ready = 0;
-            s->fuse_reduce_state = -1;
-            replayed = true;
-        }
-    }
-    if (!replayed) {
-        const bool capture = graphable && s->spec_steps_seen >= 1;
-        const int64_t launches0 = s->launches;
-        if (capture) CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = [&]() -> int {
+    {
+        bool replayed = false;
+        TRY(run_graphed(s, s->step_graphs, (uintptr_t)s->Y, speculative && graphs_on, &replayed, [&]() -> int {
             TRY(newton_step(s, 0, st));
             if (!speculative) return RST_B200_OK;
             TRY(rst_b200_reduce_local(s, 0));
@@ -1545,25 +1495,12 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
                                                           reinterpret_cast<volatile unsigned long long *>(s->h_scal + 16));
             s->launches++;
             return RST_B200_OK;
-        }();
-        if (capture) {
-            cudaGraph_t graph = nullptr;
-            const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
-            if (rc != RST_B200_OK || e != cudaSuccess || !graph) {
-                if (graph) cudaGraphDestroy(graph);
-                return rc != RST_B200_OK ? rc : fail(RST_B200_ERR_CUDA, std::string("graph capture of the damped step: ") + cudaGetErrorString(e));
-            }
-            cudaGraphExec_t exec = nullptr;
-            const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (ei != cudaSuccess) return fail(RST_B200_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei));
-            s->step_graphs[s->Y] = exec;
-            s->step_graph_launches = s->launches - launches0;
-            CUDA_TRY(cudaGraphLaunch(exec, s->stream));   // capture records, it does not run
-        } else if (rc != RST_B200_OK) {
-            return rc;
+        }));
+        if (replayed) {
+            st->linear_solves += 2;
+            s->reduce_ready = 0;
+            s->fuse_reduce_state = -1;
         }
-        if (speculative) s->spec_steps_seen++;
     }
     if (speculative) {
         // wait for the ticket of this sequence instead of synchronising the stream

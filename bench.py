@@ -8,9 +8,10 @@ Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` prints ONE 
     linear solve) + the damping reductions.  The metric is the reference's own: iterations of that loop per second
     (its story tests time whole solves and count iterations, BVP_DAMP_STORY_TESTS.md:711-732).
     The state is restored from a device-side checkpoint before every step (no host traffic in ``value``).
-  * N = 1 workload: BASELINE.json configs[1] ("c2": 2-variable BVP, 10^6 mesh points).  ``--workload c3`` times
-    configs[2] (12-variable flame, 10^6 points).  N > 1: weak scaling, every rank owns 10^6 intervals of a
-    world*10^6-point mesh (configs[3] is c3 at 10^7 points over 8 GPUs).
+  * N = 1 workload: BASELINE.json configs[1] ("c2": 2-variable BVP, 10^6 mesh points).  ``--workload c1|c3|c4|c5`` time
+    configs[0] (10^3 points), configs[2] (12-variable flame, 10^6 points), configs[3] (the flame at 10^7 points in total,
+    split over the GPUs: strong scaling) and configs[4] (64-variable coupled case, 2.5*10^5 points per GPU).  N > 1: weak
+    scaling except c4, every rank owns the per-GPU share of a world-times larger mesh.
   * ``value``   : iterations/s, state resident in HBM (CUDA events on the launching stream, max over ranks)
   * ``e2e``     : the same through the host-buffer C-ABI calls a Rust host would make per solve
                   (rst_b200_set_state H2D -> rst_b200_newton_solve -> rst_b200_get_state D2H)

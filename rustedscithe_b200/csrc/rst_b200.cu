@@ -1403,12 +1403,11 @@ static int check_scalars(const rst_b200_scalars &sc) {
 }
 
 // NRBVP::step (:1782-1847) for state `which`: dY = J^{-1} F(y)
-static int newton_step(rst_b200_solver *s, int which, rst_b200_newton_stats *st) {
+static int newton_step(rst_b200_solver *s, int which) {   // enqueue-only; the caller counts the linear solve
     TRY(rst_b200_eval_residual(s, which));
     s->fuse_reduce_state = which;  // the reduction that follows this solve refers to state `which`
     TRY(rst_b200_solve(s));
     s->fuse_reduce_state = -1;
-    st->linear_solves++;
     return RST_B200_OK;
 }
 
@@ -1426,19 +1425,31 @@ static int run_graphed(rst_b200_solver *s, std::map<uintptr_t, rst_b200_solver::
         *replayed = true;
         return RST_B200_OK;
     }
-    if (ge.seen++ < 1) return body();
+    if (ge.seen < 0 || ge.seen++ < 1) return body();   // seen < 0: capture failed once on this key, stay on direct launches
     const int64_t launches0 = s->launches;
-    CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        (void)cudaGetLastError();
+        ge.seen = -1;
+        return body();
+    }
     const int rc = body();
     cudaGraph_t graph = nullptr;
     const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
-    if (rc != RST_B200_OK || e != cudaSuccess || !graph) {
+    if (rc != RST_B200_OK) {   // a genuine error of the sequence itself (nothing has run)
         if (graph) cudaGraphDestroy(graph);
-        return rc != RST_B200_OK ? rc : fail(RST_B200_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return rc;
     }
-    const cudaError_t ei = cudaGraphInstantiate(&ge.exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ei != cudaSuccess) { ge.exec = nullptr; return fail(RST_B200_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei)); }
+    cudaError_t ei = e;
+    if (e == cudaSuccess && graph) ei = cudaGraphInstantiate(&ge.exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (ei != cudaSuccess || !ge.exec) {   // not capturable here (e.g. a stream that cannot be captured): run it directly from now on
+        (void)cudaGetLastError();
+        ge.exec = nullptr;
+        ge.seen = -1;
+        s->launches = launches0;
+        return body();
+    }
     ge.launches = s->launches - launches0;
     CUDA_TRY(cudaGraphLaunch(ge.exec, s->stream));   // capture records, it does not run
     return RST_B200_OK;
@@ -1480,7 +1491,7 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
     {
         bool replayed = false;
         TRY(run_graphed(s, s->step_graphs, (uintptr_t)s->Y, speculative && graphs_on, &replayed, [&]() -> int {
-            TRY(newton_step(s, 0, st));
+            TRY(newton_step(s, 0));
             if (!speculative) return RST_B200_OK;
             TRY(rst_b200_reduce_local(s, 0));
             set_solution_buffer(s, s->dY1);
@@ -1488,7 +1499,7 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
             newton_trial_dev_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY, s->Yt, s->d_scal, total);
             s->launches++;
             s->scal_slot = 1;
-            TRY(newton_step(s, 1, st));
+            TRY(newton_step(s, 1));
             TRY(rst_b200_reduce_local(s, 1));
             s->scal_slot = 0;
             publish_scalars_kernel<<<1, 32, 0, s->stream>>>(s->d_scal, s->h_scal, s->d_ticket,
@@ -1496,8 +1507,8 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
             s->launches++;
             return RST_B200_OK;
         }));
+        st->linear_solves += speculative ? 2 : 1;   // counted here, not in the (possibly captured / replayed) sequence
         if (replayed) {
-            st->linear_solves += 2;
             s->reduce_ready = 0;
             s->fuse_reduce_state = -1;
         }
@@ -1539,7 +1550,8 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
     while (k < o->max_damp_iter) {
         if (!(speculative && k == 0)) {
             TRY(rst_b200_make_trial(s, lambda));
-            TRY(newton_step(s, 1, st));
+            TRY(newton_step(s, 1));
+            st->linear_solves++;
             TRY(rst_b200_reduce(s, 1, &sc1));
         }
         TRY(check_scalars(sc1));

@@ -1456,7 +1456,7 @@ static int run_graphed(rst_b200_solver *s, std::map<uintptr_t, rst_b200_solver::
 }
 
 static int recalc_jacobian(rst_b200_solver *s, rst_b200_newton_stats *st) {
-    static const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;
+    const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;   // read per call: tests toggle it
     bool replayed = false;   // fixed launch sequence with fixed arguments per state buffer
     TRY(run_graphed(s, s->jac_graphs, (uintptr_t)s->Y, (s->world == 1 || s->p2p_enabled) && graphs_on, &replayed, [&]() -> int {
         TRY(rst_b200_eval_jacobian(s, 0));
@@ -1487,7 +1487,7 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
     s->scal_slot = 0;
     // The speculative sequence is ~25-45 launches with fixed arguments: small meshes are launch bound, so it is captured
     // into a CUDA graph (per Y / Y_trial parity) the second time it runs and replayed with one launch afterwards.
-    static const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;
+    const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;   // read per call: tests toggle it
     {
         bool replayed = false;
         TRY(run_graphed(s, s->step_graphs, (uintptr_t)s->Y, speculative && graphs_on, &replayed, [&]() -> int {
@@ -1647,7 +1647,7 @@ extern "C" int rst_b200_newton_frozen(rst_b200_solver *s, const rst_b200_frozen_
     rst_b200_scalars sc{};
     // device-only exchange (1 GPU or NVLink mailboxes): one iteration is an enqueue-only sequence with launch-invariant
     // arguments -> CUDA graph per (state buffer, refresh-or-not), scalars published to mapped host memory with a ticket
-    static const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;
+    const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;   // read per call: tests toggle it
     const bool fast = s->world == 1 || s->p2p_enabled;
     while (it < o->max_iterations) {
         st->iterations++;

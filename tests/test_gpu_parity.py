@@ -251,6 +251,31 @@ def test_wide_block_newton_trapezoid_matches_oracle():
     g.close()
 
 
+@pytest.mark.parametrize("key,n_steps", [("combustion6", 1000), ("coupled8", 150), ("linear2", 1000)])
+def test_graph_replay_and_direct_launches_agree(key, n_steps, monkeypatch):
+    """The damped step / Jacobian refresh are replayed as CUDA graphs from their second execution on; the same solve with
+    RST_B200_NO_GRAPH (kernel-by-kernel launches, stream-ordered) must give identical counters and a bit-identical state."""
+    spec = problems.get(key)
+    out = []
+    for no_graph in (False, True):
+        if no_graph:
+            monkeypatch.setenv("RST_B200_NO_GRAPH", "1")
+        g = _gpu(key, n_steps, guess=spec.guess(n_steps))
+        g.try_solve()
+        st = g.get_statistics()
+        out.append((st["status"], st["number of iterations"], st["number of solving linear systems"],
+                    st["number of jacobians recalculations"], g.get_state()))
+        # a second solve on the same handle replays the cached graphs from the first iteration on
+        g.set_state(spec.guess(n_steps))
+        g.try_solve()
+        st2 = g.get_statistics()
+        assert (st2["status"], st2["number of iterations"], st2["number of solving linear systems"]) == out[-1][:3]
+        assert np.array_equal(g.get_state(), out[-1][4])
+        g.close()
+    assert out[0][:4] == out[1][:4]
+    assert np.array_equal(out[0][4], out[1][4])
+
+
 def test_config_c1_closed_form():
     """examples/bvp_damped_aot_guide.rs:84-109 at N = 1000: max |y - x| < 5e-5."""
     spec = problems.get("linear2")

@@ -339,14 +339,12 @@ struct rst_b200_solver {
     bool p2p_enabled = false;
     P2pPeers peers{};
     std::vector<void *> peer_mapped;
-    unsigned long long p2p_seq = 0;
     P2pIface iface{};                  // interface system solved inside the single-CTA kernels (p2p.cuh)
     double *iface_lu = nullptr;
     int *iface_perm = nullptr;
     rst_b200_allgather_fn allgather = nullptr;
     void *allgather_ctx = nullptr;
     int64_t launches = 0;
-    cudaEvent_t ev[2]{};
     // retained create() arguments (a refined-grid handle is created from them, rst_b200_create_refined)
     std::vector<int> k_bc_var, k_bc_side;
     std::vector<double> k_bc_val, k_params, k_lo, k_hi, k_rtol;
@@ -528,8 +526,6 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
         if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail(RST_B200_ERR_CUDA, "stream"); }
         s->own_stream = true;
     }
-    cudaEventCreate(&s->ev[0]);
-    cudaEventCreate(&s->ev[1]);
 
     int rc = RST_B200_OK;
     auto build = [&]() -> int {
@@ -708,8 +704,6 @@ extern "C" void rst_b200_destroy(rst_b200_solver *s) {
     for (void *p : s->peer_mapped) cudaIpcCloseMemHandle(p);
     for (void *p : s->owned) cudaFree(p);
     if (s->h_scal) cudaFreeHost(s->h_scal);
-    if (s->ev[0]) cudaEventDestroy(s->ev[0]);
-    if (s->ev[1]) cudaEventDestroy(s->ev[1]);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -1074,8 +1068,7 @@ extern "C" int rst_b200_factor_local(rst_b200_solver *s) {
             s->launches++;
         }
         const bool fused = fused_p2p(s);
-        if (fused) s->p2p_seq++;
-        tps_tail_factor_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, iface_args(s, fused), s->p2p_seq, s->d_flags);
+        tps_tail_factor_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, iface_args(s, fused), 0ull /* sequence number lives on the device (P2pPeers::seq_dev) */, s->d_flags);
         s->launches++;
         CUDA_TRY(cudaGetLastError());
         return RST_B200_OK;
@@ -1112,9 +1105,8 @@ extern "C" int rst_b200_factor_reduced(rst_b200_solver *s) {
 // all-gather of `count` doubles per rank: NVLink peer-memory kernel when the peers are mapped, host callback otherwise
 static int exchange(rst_b200_solver *s, const double *send, double *recv, int64_t count) {
     if (s->p2p_enabled) {
-        s->p2p_seq++;
         p2p_allgather_kernel<<<1, 256, 0, s->stream>>>(s->peers, send, (int)count, recv, s->rank, s->world, s->p2p_pay,
-                                                       s->p2p_seq, s->d_flags);
+                                                       0ull /* sequence number lives on the device (P2pPeers::seq_dev) */, s->d_flags);
         s->launches++;
         CUDA_TRY(cudaGetLastError());
         return RST_B200_OK;
@@ -1203,9 +1195,8 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
     if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
     if (s->use_tps && (s->world == 1 || fused_p2p(s))) {
         const bool fused = fused_p2p(s);
-        if (fused) s->p2p_seq++;
         // forward sweeps -> closure (1 GPU) or NVLink interface exchange + solve (multi GPU) -> backward sweeps: ONE launch
-        tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, iface_args(s, fused), s->p2p_seq,
+        tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, iface_args(s, fused), 0ull /* sequence number lives on the device (P2pPeers::seq_dev) */,
                                                                    fused ? 13 : 7, s->d_flags);
         s->launches++;
         for (int i = (int)s->tps_big.size() - 1; i >= 0; --i) {
@@ -1322,9 +1313,8 @@ extern "C" int rst_b200_reduce_local(rst_b200_solver *s, int which_state) {
     }
     s->reduce_ready = 0;
     const bool fused_red = s->p2p_enabled && s->world > 1;
-    if (fused_red) s->p2p_seq++;
     newton_reduce_final_kernel<<<1, 256, 0, s->stream>>>(s->d_partials, nblocks, s->d_scal + 8 * s->scal_slot, s->d_flags, s->peers, s->rank,
-                                                         fused_red ? s->world : 1, s->p2p_pay, s->p2p_seq, s->d_gscal);
+                                                         fused_red ? s->world : 1, s->p2p_pay, 0ull /* sequence number lives on the device (P2pPeers::seq_dev) */, s->d_gscal);
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return RST_B200_OK;

@@ -65,3 +65,47 @@ def test_custom_problem_solves_to_the_discrete_closed_form(artifact):
     assert np.max(np.abs(full[:, 1] - 2.0 * j * h)) < 1e-11
     assert np.max(np.abs(full[:, 0] - h * h * j * (j - 1))) < 1e-11
     g.close()
+
+
+# ---- wide custom problems: block sizes between the compiled-in ones (odd nv -> generation-1 sweeps, padded register tiles) ----
+def _chains_spec(key, n_chains, length):
+    """`n_chains` independent integrator chains y_0' = y_1, ..., y_{L-1}' = 0 with y_i(0) = 0 (i < L-1), y_{L-1}(1) = c_b:
+    forward Euler gives y_{L-1-m}(x_j) = c_b h^m C(j, m) exactly (repeated summation of a constant)."""
+    names = [f"y{b}_{i}" for b in range(n_chains) for i in range(length)]
+
+    def rhs():
+        import sympy as sp
+        s = [sp.Symbol(n, real=True) for n in names]
+        out = []
+        for b in range(n_chains):
+            for i in range(length):
+                out.append(s[b * length + i + 1] if i + 1 < length else sp.Float(0.0))
+        return out
+
+    bcs = {}
+    for b in range(n_chains):
+        for i in range(length):
+            bcs[names[b * length + i]] = [(0, 0.0)] if i + 1 < length else [(1, 1.0 + 0.5 * b)]
+    return problems.ProblemSpec(key=key, names=names, rhs=rhs, bcs=bcs, bounds={n: (-1e6, 1e6) for n in names},
+                                rtol={n: 1e-8 for n in names}, guess=lambda n, nv=len(names): np.full(nv * n, 0.1),
+                                abs_tol=1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key,n_chains,length,n", [("chains21", 3, 7, 90), ("chains40", 5, 8, 70)])
+def test_wide_custom_problems_solve_to_the_discrete_closed_form(key, n_chains, length, n):
+    from math import comb
+    from rustedscithe_b200.solver import NRBVP, DampedSolverOptions
+    spec = _chains_spec(key, n_chains, length)
+    rbuild.build_artifact(spec, "build_if_missing")
+    g = NRBVP(spec, spec.guess(n), n, DampedSolverOptions.from_spec(spec, slab=4))
+    assert g.try_solve() is not None
+    full = g.get_result()
+    h = 1.0 / n
+    for b in range(n_chains):
+        c = 1.0 + 0.5 * b
+        for m in range(length):
+            exact = np.array([c * h ** m * comb(j, m) for j in range(n + 1)])
+            col = full[:, b * length + (length - 1 - m)]
+            assert np.max(np.abs(col - exact)) <= 1e-10 * max(1.0, np.max(np.abs(exact))), (b, m)
+    g.close()

@@ -178,12 +178,17 @@ struct SolverImpl {
     static SolverVT vt() { return SolverVT{NV, &factor, &forward, &backward, &top, &residual, &reduce, &top_general}; }
 };
 
+// "dynamic shared memory limit raised" flags of the wide-block kernels.  They MUST have internal linkage: function-local
+// statics of inline / template functions are STB_GNU_UNIQUE symbols, i.e. ONE object per process even across dlopen'ed
+// libraries -- a second library (AOT artefact) would then skip cudaFuncSetAttribute for ITS copy of the kernel and fail to launch.
+static bool g_big_attr_done[8] = {false, false, false, false, false, false, false, false};
+
 // wide blocks (16 < nv <= 64, or any nv >= 3 with RST_B200_FORCE_BIG): run-time-nv block-per-slab kernels (big.cuh)
 struct BigImpl {
     template <int NVP, int NW>
     static void factor_tiled(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
         using C = BigrCfg<NVP, NW>;
-        static bool attr_set = false;
+        bool &attr_set = g_big_attr_done[(NVP > 32 ? 1 : 0) + (NW > 16 ? 2 : 0)];
         if (!attr_set) {
             cudaFuncSetAttribute(bigr_factor_kernel<NVP, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
             cudaFuncSetAttribute(bigr_factor_kernel<NVP, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
@@ -205,7 +210,7 @@ struct BigImpl {
             return;
         }
         const size_t smem = big_factor_smem_bytes(L.nv);
-        static bool attr_set = false;
+        bool &attr_set = g_big_attr_done[4];
         if (!attr_set) {
             cudaFuncSetAttribute(big_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_factor_smem_bytes(BIG_MAX_NV));
             cudaFuncSetAttribute(big_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_factor_smem_bytes(BIG_MAX_NV));
@@ -225,7 +230,7 @@ struct BigImpl {
             big_forward_kernel<<<(unsigned)L.nslabs, 128, 0, st>>>(L, L.nv);
             return;
         }
-        static bool attr_set = false;
+        bool &attr_set = g_big_attr_done[5];
         if (!attr_set) {
             cudaFuncSetAttribute(bigp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bigp_forward_smem(BIG_MAX_NV));
             attr_set = true;
@@ -237,7 +242,7 @@ struct BigImpl {
             big_backward_kernel<<<(unsigned)L.nslabs, 64, 0, st>>>(L, L.nv);
             return;
         }
-        static bool attr_set = false;
+        bool &attr_set = g_big_attr_done[6];
         if (!attr_set) {
             cudaFuncSetAttribute(bigp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bigp_backward_smem(BIG_MAX_NV));
             attr_set = true;
@@ -399,7 +404,8 @@ static int dev_alloc(H *s, T **p, size_t count) {
 
 static int default_slab(int64_t n, int requested) {
     if (requested >= 2) return requested;
-    if (n >= (1 << 17)) return 32;
+    // measured at nv = 12, 1e6 rows (solve ms): S = 8 1.090, 12 1.065, 16 1.049, 32 1.078, 64 1.107 -- longer slabs mean fewer
+    // levels but a longer dependent chain per warp; nv = 64: 16 beats 32 as well
     if (n >= (1 << 12)) return 16;
     return 8;
 }

@@ -104,3 +104,17 @@ def test_emitted_literals_round_trip_exactly():
     em = emit_problem(problems.get("combustion6"))
     for lit in re.findall(r"[-+]?\d\.\d{17}e[-+]\d{2}", em.source):
         assert float("%.17e" % float(lit)) == float(lit)
+
+
+def test_grid_method_numbers_match_the_header():
+    """solver.GRID_METHODS (host mirror of GridRefinementMethod, grid_api.rs:62-115) and the RST_B200_GRID_* defines agree."""
+    import os
+    import re
+    from rustedscithe_b200 import solver
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "rst_b200.h")).read()
+    defines = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define RST_B200_GRID_([A-Z_]+) (\d+)", hdr)}
+    names = {"DoublePoints": "DOUBLE_POINTS", "Easy": "EASY", "Pearson": "PEARSON", "GrcarSmooke": "GRCAR_SMOOKE", "Sci": "SCI"}
+    assert {names[k]: v for k, v in solver.GRID_METHODS.items()} == defines
+    from oracle import adaptive_grid as ag
+    assert [ag.DOUBLE_POINTS, ag.EASY, ag.PEARSON, ag.GRCAR_SMOOKE, ag.SCI] == [defines[n] for n in
+                                                                               ("DOUBLE_POINTS", "EASY", "PEARSON", "GRCAR_SMOOKE", "SCI")]

@@ -139,7 +139,7 @@ def run_reference(args, rank, world):
     spec = problems.get(key)
     n = min(n_local, args.cpu_points or n_cpu)
     run = _oracle_solve(key, n, spec)
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(2 if args.warmup >= 1 else 0):   # the first TWO oracle solves are slow (OpenMP pool start-up, first touch)
         run()
     times, res = [], None
     for _ in range(args.steps):
@@ -392,7 +392,8 @@ def main():
             from oracle import oracle as orc
             n_c = min(n_local, args.cpu_points or n_cpu)
             run = _oracle_solve(key, n_c, spec)
-            run()   # untimed: first-touch page faults and OpenMP start-up make the first solve up to 2x slower
+            run()   # untimed: first-touch page faults and OpenMP pool start-up make the first two solves slower
+            run()
             tt, reps_cpu, res = time.perf_counter(), 0, None
             while reps_cpu < 3 and time.perf_counter() - tt < 20.0:
                 _, res = run()

@@ -139,8 +139,9 @@ def run_reference(args, rank, world):
     spec = problems.get(key)
     n = min(n_local, args.cpu_points or n_cpu)
     run = _oracle_solve(key, n, spec)
-    for _ in range(2 if args.warmup >= 1 else 0):   # the first TWO oracle solves are slow (OpenMP pool start-up, first touch)
-        run()
+    if args.warmup >= 1:   # the first TWO oracle solves are slow (OpenMP pool start-up, first touch)
+        if run()[0] < 3.0:
+            run()
     times, res = [], None
     for _ in range(args.steps):
         dt, res = run()
@@ -392,8 +393,8 @@ def main():
             from oracle import oracle as orc
             n_c = min(n_local, args.cpu_points or n_cpu)
             run = _oracle_solve(key, n_c, spec)
-            run()   # untimed: first-touch page faults and OpenMP pool start-up make the first two solves slower
-            run()
+            if run()[0] < 3.0:   # untimed: OpenMP pool start-up and first touch make the first two solves slower;
+                run()            # one is enough when a solve takes seconds
             tt, reps_cpu, res = time.perf_counter(), 0, None
             while reps_cpu < 3 and time.perf_counter() - tt < 20.0:
                 _, res = run()

@@ -155,33 +155,54 @@ template <int NV>
 __device__ void iface_solve_block(const P2pIface &I, unsigned long long seq, unsigned *flags) {
     constexpr int MMAX = (P2P_MAX_WORLD + 1) * NV;
     __shared__ double b[MMAX];
+    __shared__ double lu_s[MMAX][MMAX + 1];
+    __shared__ int perm_s[MMAX];
     const int m = (I.world + 1) * NV;
+    // the factors of the interface system come from HBM once, BEFORE the exchange (their latency hides behind the wait for
+    // the peers); substituting straight from global memory cost one dependent round trip per row (~18 us at 8 ranks)
+    for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) lu_s[idx / m][idx % m] = I.lu[idx];
+    for (int k = threadIdx.x; k < m; k += blockDim.x) perm_s[k] = I.perm[k];
     p2p_allgather_block(I.peers, I.rhs_send, NV, I.rhs_gath, I.rank, I.world, I.pay, seq, flags);
     for (int i = threadIdx.x; i < m; i += blockDim.x) b[i] = i < I.world * NV ? I.rhs_gath[i] : 0.0;
     __syncthreads();
-    if (threadIdx.x < 32) {  // one warp: row swaps, unit-lower then upper substitution with warp dot products
+    if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         if (lane == 0)
             for (int k = 0; k < m; ++k) {
-                const int p = I.perm[k];
+                const int p = perm_s[k];
                 if (p != k) { const double t = b[k]; b[k] = b[p]; b[p] = t; }
             }
         __syncwarp();
-        for (int i = 1; i < m; ++i) {
-            double s = 0.0;
-            for (int j = lane; j < i; j += 32) s = fma(I.lu[(size_t)i * m + j], b[j], s);
+        if (m <= 32) {
+            // lane = row: column-oriented substitution, one shuffle + one FMA per step, no reductions
+            double bi = lane < m ? b[lane] : 0.0;
+            for (int k = 0; k + 1 < m; ++k) {
+                const double bk = __shfl_sync(RST_FULL_MASK, bi, k);
+                if (lane > k && lane < m) bi = fma(-lu_s[lane][k], bk, bi);
+            }
+            for (int k = m - 1; k >= 0; --k) {
+                if (lane == k) bi = bi / lu_s[k][k];
+                const double xk = __shfl_sync(RST_FULL_MASK, bi, k);
+                if (lane < k) bi = fma(-lu_s[lane][k], xk, bi);
+            }
+            if (lane < m) b[lane] = bi;
+        } else {  // more than 32 interface unknowns: row-oriented with warp dot products (from shared memory)
+            for (int i = 1; i < m; ++i) {
+                double sacc = 0.0;
+                for (int j = lane; j < i; j += 32) sacc = fma(lu_s[i][j], b[j], sacc);
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(RST_FULL_MASK, s, off);
-            if (lane == 0) b[i] -= s;
-            __syncwarp();
-        }
-        for (int i = m - 1; i >= 0; --i) {
-            double s = 0.0;
-            for (int j = i + 1 + lane; j < m; j += 32) s = fma(I.lu[(size_t)i * m + j], b[j], s);
+                for (int off = 16; off >= 1; off >>= 1) sacc += __shfl_xor_sync(RST_FULL_MASK, sacc, off);
+                if (lane == 0) b[i] -= sacc;
+                __syncwarp();
+            }
+            for (int i = m - 1; i >= 0; --i) {
+                double sacc = 0.0;
+                for (int j = i + 1 + lane; j < m; j += 32) sacc = fma(lu_s[i][j], b[j], sacc);
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(RST_FULL_MASK, s, off);
-            if (lane == 0) b[i] = (b[i] - s) / I.lu[(size_t)i * m + i];
-            __syncwarp();
+                for (int off = 16; off >= 1; off >>= 1) sacc += __shfl_xor_sync(RST_FULL_MASK, sacc, off);
+                if (lane == 0) b[i] = (b[i] - sacc) / lu_s[i][i];
+                __syncwarp();
+            }
         }
     }
     __syncthreads();

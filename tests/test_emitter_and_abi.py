@@ -118,3 +118,42 @@ def test_grid_method_numbers_match_the_header():
     from oracle import adaptive_grid as ag
     assert [ag.DOUBLE_POINTS, ag.EASY, ag.PEARSON, ag.GRCAR_SMOOKE, ag.SCI] == [defines[n] for n in
                                                                                ("DOUBLE_POINTS", "EASY", "PEARSON", "GRCAR_SMOOKE", "SCI")]
+
+
+@pytest.mark.parametrize("key", ["damp1p", "flame12", "coupled64"])
+def test_emitted_cuda_c_text_evaluates_like_the_oracle_on_the_host(key, tmp_path):
+    """The emitted struct is plain C++ apart from the CUDA qualifiers: compiled for the host (g++) it must reproduce the
+    hand-written oracle right-hand side and Jacobian -- dense `eval_f_fy` for narrow problems, the sink form `eval_f_nz`
+    for wide ones -- so the generated TEXT is pinned on the CPU, not only its sympy source."""
+    import ctypes
+    import subprocess
+    spec = problems.get(key)
+    em = emit_problem(spec)
+    nv = spec.nv
+    wide = "eval_f_nz" in em.source
+    body = ("HostSink s{J}; P::eval_f_nz(t, y, p, f, s);" if wide else "P::eval_f_fy(t, y, p, f, J);")
+    src = tmp_path / f"{key}.cpp"
+    src.write_text(
+        "#include <cmath>\nusing std::exp; using std::log; using std::sin; using std::cos; using std::tan; using std::pow;\n"
+        "using std::sqrt; using std::asin; using std::acos; using std::atan;\n"
+        "#define __device__\n#define __forceinline__ inline\n" + em.source +
+        f"\nusing P = Problem_{key};\nstruct HostSink {{ double *J; void put(int idx, double v) {{ J[idx] = v; }} }};\n"
+        "extern \"C\" void eval_host(double t, const double *y, const double *p, double *f, double *f_only, double *J) {\n"
+        f"    for (int i = 0; i < {nv * nv}; ++i) J[i] = 0.0;\n    {body}\n    P::eval_f(t, y, p, f_only);\n}}\n")
+    lib = tmp_path / f"{key}.so"
+    subprocess.run(["/usr/bin/g++", "-O0", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(lib), str(src)], check=True)
+    L = ctypes.CDLL(str(lib))
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.eval_host.argtypes = [ctypes.c_double, dp, dp, dp, dp, dp]
+    rng = np.random.default_rng(8)
+    yv = np.ascontiguousarray(0.3 + 0.5 * rng.random(nv))
+    pv = np.ascontiguousarray(list(spec.param_values) or [0.0], dtype=np.float64)
+    f, f_only, J = np.zeros(nv), np.zeros(nv), np.zeros(nv * nv)
+    L.eval_host(0.37, yv.ctypes.data_as(dp), pv.ctypes.data_as(dp), f.ctypes.data_as(dp), f_only.ctypes.data_as(dp),
+                J.ctypes.data_as(dp))
+    f_orc, J_orc = orc.problem_rhs(key, 0.37, yv, list(spec.param_values) or None)
+    scale_f = np.abs(f_orc) + 1e-12 * np.max(np.abs(f_orc)) + 1e-300
+    assert np.max(np.abs(f - f_orc) / scale_f) < 1e-12 and np.max(np.abs(f_only - f_orc) / scale_f) < 1e-12
+    J = J.reshape(nv, nv)
+    assert np.max(np.abs(J - J_orc) / (np.abs(J_orc) + 1e-12 * np.max(np.abs(J_orc)) + 1e-300)) < 1e-12
+    assert np.array_equal(J != 0.0, np.array(em.pattern).reshape(nv, nv) != 0)

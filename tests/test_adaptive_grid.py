@@ -123,6 +123,20 @@ def test_oracle_scipy_residual_thresholds_insert_expected_nodes():
         assert np.any(np.abs(refined[0] - expected) <= 1e-14)
 
 
+@pytest.mark.parametrize("method,params", [(ag.DOUBLE_POINTS, ())] + CASES + [(ag.PEARSON, (1e-3, 1.4)), (ag.GRCAR_SMOOKE, (1e-3, 1e-2, 1.4))])
+def test_oracle_invariants_on_a_nonuniform_mesh(method, params):
+    """The refinement invariants of the reference's tests (:1042-1115) on a graded mesh (the hand-off after a first
+    refinement always sees one), incl. the production parameter sets of the user guide (delta 1e-3, ratio 1.4)."""
+    rng = np.random.default_rng(12)
+    w = rng.uniform(0.2, 3.0, 47)
+    x = np.concatenate([[0.0], np.cumsum(w) / np.sum(w)])
+    x[-1] = 1.0
+    y = np.stack([1.2 + np.tanh(18.0 * (x - 0.38)), 0.8 + np.sin(7.0 * x) + 0.15 * x, 0.2 + np.exp(-70.0 * (x - 0.72) ** 2)])
+    refined = ag.new_grid(method, y, x, params=params)
+    assert_refinement_invariants(y, x, refined)
+    assert refined[2] == int(np.sum(refined[3][:-1]))          # inserted nodes = sum of the marks that can be honoured
+
+
 def test_oracle_rust_cast_semantics():
     assert ag._as_i32(3.99) == 3 and ag._as_i32(float("inf")) == 2147483647 and ag._as_i32(float("nan")) == 0
 

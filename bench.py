@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--points", type=int, default=0, help="override intervals per GPU")
     ap.add_argument("--cpu-points", type=int, default=0, help="mesh size of the CPU sample (default per workload)")
     ap.add_argument("--slab", type=int, default=0)

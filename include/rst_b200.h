@@ -204,6 +204,16 @@ int rst_b200_set_allgather(rst_b200_solver *s, rst_b200_allgather_fn fn, void *c
  * _solve / _reduce run the all-gather as a small kernel on the solver's own stream -- no host callback, no NCCL. */
 int rst_b200_p2p_get_handle(rst_b200_solver *s, void *handle_out, size_t handle_bytes);
 int rst_b200_p2p_open(rst_b200_solver *s, const void *handles /* [world][handle_stride] */, size_t handle_stride);
+/* Wire format: every 8-byte word carries its own 32-bit sequence tag (a double travels as two flagged words), so no
+ * store wider than the architecture's single-copy-atomic unit has to arrive untorn.  A rank that waits longer than
+ * RST_B200_PEER_TIMEOUT_MS (environment, default 30000) for a peer poisons its handle: the exchange returns NaN words,
+ * every later reduction reports RST_B200_ERR_CUDA.  Callers barrier once after rst_b200_p2p_open (all ranks mapped)
+ * before the first factorisation.
+ * rst_b200_p2p_selftest: `world` emulated ranks (one CTA each, ONE cooperative launch on `device`) run `rounds`
+ * back-to-back gathers through the same device function the solver uses; every received word is checked bit for bit.
+ * absent_rank >= 0: that rank never arrives -- the others must time out (timeout_ms), flag it and receive NaN. */
+int rst_b200_p2p_selftest(int device, int world, int rounds, int pay, int absent_rank, double timeout_ms,
+                          int64_t *mismatches, int64_t *nan_words, int *ranks_timed_out);
 /* local intervals [begin, end) of this rank */
 int rst_b200_dist_range(const rst_b200_solver *s, int64_t *j_begin, int64_t *j_end);
 /* phase-split primitives (rst_b200_factor / _solve / _reduce call them around the all-gather callback;

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) newton_reduce_final_kernel(const double *
             b0 += sh[0][i]; b1 += sh[1][i]; b2 = fmin(b2, sh[2][i]); b3 = fmax(b3, sh[3][i]);
         }
         out[0] = b0; out[1] = b1; out[2] = b2; out[3] = b3;
-        out[4] = (double)(*flags);
+        out[4] = (double)(flags[0] | flags[2]);   // flags[2]: sticky (peer timeout poisons the handle)
         out[5] = 0.0; out[6] = 0.0; out[7] = 0.0;
     }
     if (world > 1) {
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) newton_reduce_final_kernel(const double *
                 c3 = fmax(c3, gscal[8 * p + 3]); c4 = fmax(c4, gscal[8 * p + 4]);
             }
             out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-            out[4] = fmax(c4, (double)(*flags));
+            out[4] = fmax(c4, (double)(flags[0] | flags[2]));
         }
     }
 }

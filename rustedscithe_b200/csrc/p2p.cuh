@@ -5,13 +5,17 @@
 // 8 damping scalars per trial.  Through NCCL + a host callback each of them costs ~25 us of launch/host latency,
 // which is a quarter of a 1 ms Newton solve at C2.  Here every rank owns a "mailbox" in its HBM that its peers map
 // through CUDA IPC; the gather is ONE small kernel per rank on the solver's own stream:
-//   1. store my payload into slot [parity][my_rank] of every peer's mailbox (peer stores travel over NVLink) as 16-byte
-//      (value, sequence number) pairs -- one aligned vector store each, so a value and its tag arrive together and no
-//      fence + separate flag round trip is needed (the low-latency "LL" protocol of collective libraries),
-//   2. spin on every pair of my own mailbox until its tag equals the sequence number, keep the value.
+//   1. store my payload into slot [parity][my_rank] of every peer's mailbox (peer stores travel over NVLink),
+//   2. spin on my own mailbox until every word carries the tag of this exchange, keep the values.
+// Wire format (the "LL" protocol of collective libraries): PTX guarantees single-copy atomicity per 8-byte element
+// only, so EVERY 8-byte word carries its own flag -- a double travels as two words
+//       word0 = (low 32 bits of the value)  | (tag << 32)      word1 = (high 32 bits) | (tag << 32)
+// with tag = low 32 bits of the exchange sequence number.  A word whose tag matches is complete by itself: no fence, no
+// separate flag round trip, and a torn 16-byte store can at worst delay one half, never pair a stale half with a fresh
+// tag.  (Round 1 sent (value, tag) as one 16-byte store and relied on it arriving untorn.)
 // One process per GPU, so the kernels of different ranks always run concurrently (each on its own device); slots are
 // double-buffered by the parity of the sequence number: a rank cannot run two gathers ahead of a peer because it
-// waits for that peer's flag of the gather in between.
+// waits for that peer's words of the gather in between.
 #pragma once
 #include "rst_common.cuh"
 
@@ -24,18 +28,25 @@ struct P2pPeers {
     // exchange sequence number, kept on the DEVICE (every rank runs the same exchanges in stream order, so the local
     // counters agree): kernel arguments stay constant from launch to launch and the sequences can be replayed as CUDA graphs
     unsigned long long *seq_dev;
+    // spin budget in clock cycles before a missing peer is reported (RST_FLAG_PEER_TIMEOUT); the handle is then poisoned:
+    // the received values are NaN, never stale data
+    long long timeout_cycles;
 };
 
-// mailbox layout: pairs[2][world][pay] of (value, tag) = 2 doubles each
+// mailbox layout: words[2 parities][world][pay][2] of 8 bytes
 __host__ __device__ inline size_t p2p_mailbox_doubles(int world, int pay) { return (size_t)2 * 2 * world * pay; }
 
-__device__ __forceinline__ void st_pair_sys(double *p, double v, unsigned long long tag) {
-    asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
+__device__ __forceinline__ void st_ll_pair(double *p, double v, unsigned tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long t = (unsigned long long)tag << 32;
+    const unsigned long long w0 = (b & 0xffffffffull) | t, w1 = (b >> 32) | t;
+    asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ void ld_pair_sys(const double *p, double &v, unsigned long long &tag) {
-    long long a;
-    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(tag) : "l"(p) : "memory");
-    v = __longlong_as_double(a);
+__device__ __forceinline__ bool ld_ll_pair(const double *p, unsigned tag, double &v) {
+    unsigned long long w0, w1;
+    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    return (unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag;
 }
 
 // The gather as a block-wide device function (every thread of ONE CTA calls it): used stand-alone below and fused into
@@ -49,24 +60,26 @@ __device__ __forceinline__ void p2p_allgather_block(const P2pPeers &peers, const
     if (threadIdx.x == 0) seq_sh = *peers.seq_dev + 1ull;
     __syncthreads();
     seq = seq_sh;
+    const unsigned tag = (unsigned)seq;
     const int parity = (int)(seq & 1ull);
-    const size_t slot = ((size_t)parity * world + my_rank) * pay * 2;          // in doubles: pairs of (value, tag)
+    const size_t slot = ((size_t)parity * world + my_rank) * pay * 2;          // in doubles: two words per value
     for (int p = 0; p < world; ++p) {
         double *dst = peers.mailbox[p] + slot;
-        for (int i = threadIdx.x; i < count; i += blockDim.x) st_pair_sys(dst + 2 * i, send[i], seq);
+        for (int i = threadIdx.x; i < count; i += blockDim.x) st_ll_pair(dst + 2 * i, send[i], tag);
     }
     const double *mine = peers.mailbox[my_rank] + (size_t)parity * world * pay * 2;
+    const long long budget = peers.timeout_cycles > 0 ? peers.timeout_cycles : 60000000000ll;   // default ~30 s
     for (int idx = threadIdx.x; idx < world * count; idx += blockDim.x) {
         const int p = idx / count, i = idx - p * count;
         const double *src = mine + ((size_t)p * pay + i) * 2;
         double v;
-        unsigned long long tag;
         const long long t0 = clock64();
         for (;;) {
-            ld_pair_sys(src, v, tag);
-            if (tag == seq) break;
-            if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer never arrived
+            if (ld_ll_pair(src, tag, v)) break;
+            if (clock64() - t0 > budget) {  // a peer never arrived: poison, do not hand out stale data
                 atomicOr(flags, RST_FLAG_PEER_TIMEOUT);
+                atomicOr(flags + 2, RST_FLAG_PEER_TIMEOUT);   // sticky word: survives the per-factorisation reset of flags[0]
+                v = __longlong_as_double(0x7ff8000000000000ll);
                 break;
             }
         }
@@ -81,6 +94,50 @@ __global__ void __launch_bounds__(256) p2p_allgather_kernel(P2pPeers peers, cons
                                                             double *__restrict__ recv, int my_rank, int world, int pay,
                                                             unsigned long long seq, unsigned *flags) {
     p2p_allgather_block(peers, send, count, recv, my_rank, world, pay, seq, flags);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Self-test of the exchange protocol on ONE device: CTA p plays rank p (own mailbox, own sequence counter, the same
+// p2p_allgather_block the solver uses), `rounds` back-to-back gathers with round-dependent payloads and sizes, every
+// received word checked bit for bit.  One cooperative launch, so the CTAs are co-resident by construction (spin-waiting
+// kernels must never be separate launches on one GPU).  `absent` >= 0: that rank never shows up -> the others must report
+// RST_FLAG_PEER_TIMEOUT and receive NaN for its words instead of stale data.
+// ------------------------------------------------------------------------------------------------
+struct P2pSelfTest {
+    P2pPeers peers[P2P_MAX_WORLD];   // per emulated rank (they differ in seq_dev)
+    double *send;                    // [world][pay]
+    double *recv;                    // [world][world * pay]
+    unsigned *flags;                 // [world][4]
+    unsigned long long *mismatches;  // [1]
+    unsigned long long *nan_words;   // [1] words received as NaN (timeout path)
+    int world, pay, rounds, absent;
+    int counts[3];
+};
+
+__device__ __forceinline__ double p2p_selftest_value(int rank, int round, int i) {
+    // distinct bit patterns in both 32-bit halves
+    const unsigned long long x = 0x9E3779B97F4A7C15ull * (unsigned long long)(1 + rank + 17 * (i + 131 * round)) + 0x1234567ull * i;
+    return __longlong_as_double((long long)((x & 0x800fffffffffffffull) | 0x3ff0000000000000ull));
+}
+
+__global__ void __launch_bounds__(256) p2p_selftest_kernel(P2pSelfTest t) {
+    const int rank = blockIdx.x;
+    if (rank == t.absent) return;
+    double *send = t.send + (size_t)rank * t.pay;
+    double *recv = t.recv + (size_t)rank * t.world * t.pay;
+    for (int r = 0; r < t.rounds; ++r) {
+        const int count = t.counts[r % 3];
+        for (int i = threadIdx.x; i < count; i += blockDim.x) send[i] = p2p_selftest_value(rank, r, i);
+        p2p_allgather_block(t.peers[rank], send, count, recv, rank, t.world, t.pay, 0ull, t.flags + 4 * rank);
+        for (int idx = threadIdx.x; idx < t.world * count; idx += blockDim.x) {
+            const int p = idx / count, i = idx - p * count;
+            const double got = recv[idx], want = p2p_selftest_value(p, r, i);
+            if (got != got) atomicAdd(t.nan_words, 1ull);
+            else if (__double_as_longlong(got) != __double_as_longlong(want)) atomicAdd(t.mismatches, 1ull);
+        }
+        __syncthreads();
+        if (t.flags[4 * rank + 2] != 0u) return;   // poisoned: stop (every later gather would time out as well)
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@
 
 #include "abd.cuh"
 #include "abd3.cuh"
+#include "abd4.cuh"
 #include "tps.cuh"
 #include "btd.cuh"
 #include "p2p.cuh"
@@ -127,7 +128,8 @@ static int kernel_generation() {
     static int gen = [] {
         const char *e = std::getenv("RST_B200_KERNELS");
         if (e && std::strcmp(e, "v1") == 0) return 1;
-        return 3;  // abd3.cuh: one row per lane, REDUX pivot search, shared-memory broadcast, reciprocal multipliers
+        if (e && std::strcmp(e, "v3") == 0) return 3;  // abd3.cuh: one row per lane, REDUX pivot search, shared-memory broadcast
+        return 4;  // abd4.cuh (nv = 8, 12, 16): blocked elimination, rank-4 updates on the FP64 tensor cores; abd3.cuh otherwise
     }();
     return gen;
 }
@@ -139,7 +141,18 @@ struct SolverImpl {
         const int64_t per_block = 4 * gpw;
         return (unsigned)((nslabs + per_block - 1) / per_block);
     }
+    // generation 4 (abd4.cuh) changes the multiplier layout: factor and forward sweep switch together
+    static constexpr bool HAS_V4 = (NV % 4 == 0) && NV >= 8 && NV <= 16;
+    static bool use_v4() { return HAS_V4 && kernel_generation() >= 4; }
     static void factor(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
+        if constexpr (HAS_V4) {
+            if (use_v4()) {
+                const unsigned blocks = (unsigned)((L.nslabs + 3) / 4);
+                if (ident_b) abd_factor4_kernel<NV, true><<<blocks, 128, 0, st>>>(L, flags);
+                else abd_factor4_kernel<NV, false><<<blocks, 128, 0, st>>>(L, flags);
+                return;
+            }
+        }
         // REDUX with several sub-warp masks serialises per mask: generation 3 only where a slab spans >= 16 lanes
         if constexpr (NV % 2 == 0) {
             if (kernel_generation() >= 2 && NV >= 6) {
@@ -154,6 +167,12 @@ struct SolverImpl {
         else abd_factor_kernel<NV, false><<<blocks, 128, 0, st>>>(L, flags);
     }
     static void forward(const AbdLevel &L, cudaStream_t st) {
+        if constexpr (HAS_V4) {
+            if (use_v4()) {
+                abd_forward4_kernel<NV><<<(unsigned)((L.nslabs + 3) / 4), 128, 0, st>>>(L);
+                return;
+            }
+        }
         abd_forward_kernel<NV><<<grid_for(L.nslabs, 2 * NV), 128, 0, st>>>(L);
     }
     static void backward(const AbdLevel &L, cudaStream_t st) {
@@ -1126,10 +1145,71 @@ static int exchange(rst_b200_solver *s, const double *send, double *recv, int64_
 extern "C" int rst_b200_p2p_get_handle(rst_b200_solver *s, void *handle_out, size_t handle_bytes) {
     if (!s || !handle_out || handle_bytes < sizeof(cudaIpcMemHandle_t)) return fail(RST_B200_ERR_INVALID, "bad handle buffer");
     if (!s->mailbox) return fail(RST_B200_ERR_INVALID, "world == 1 has no mailbox");
+    CUDA_TRY(cudaStreamSynchronize(s->stream));   // the mailbox must be zeroed before any peer can see it
     cudaIpcMemHandle_t h;
     CUDA_TRY(cudaIpcGetMemHandle(&h, s->mailbox));
     std::memcpy(handle_out, &h, sizeof(h));
     return RST_B200_OK;
+}
+
+// protocol self-test on one device (p2p.cuh): `world` emulated ranks in one cooperative launch
+extern "C" int rst_b200_p2p_selftest(int device, int world, int rounds, int pay, int absent_rank, double timeout_ms,
+                                     int64_t *mismatches, int64_t *nan_words, int *timeout_flags) {
+    if (world < 2 || world > P2P_MAX_WORLD || rounds < 1 || pay < 8) return fail(RST_B200_ERR_INVALID, "bad self-test arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    int coop = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!coop) return fail(RST_B200_ERR_UNSUPPORTED, "device cannot launch cooperatively");
+    P2pSelfTest t{};
+    std::vector<void *> owned;
+    auto alloc = [&](size_t bytes) -> void * {
+        void *q = nullptr;
+        if (cudaMalloc(&q, bytes) != cudaSuccess) return nullptr;
+        cudaMemset(q, 0, bytes);
+        owned.push_back(q);
+        return q;
+    };
+    int khz = 1965000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    bool ok = true;
+    const size_t mb = p2p_mailbox_doubles(world, pay);
+    double *boxes[P2P_MAX_WORLD] = {};
+    for (int p = 0; p < world; ++p) ok = ok && (boxes[p] = (double *)alloc(mb * sizeof(double)));
+    unsigned long long *seqs = (unsigned long long *)alloc(sizeof(unsigned long long) * world);
+    t.send = (double *)alloc(sizeof(double) * world * pay);
+    t.recv = (double *)alloc(sizeof(double) * world * world * pay);
+    t.flags = (unsigned *)alloc(sizeof(unsigned) * 4 * world);
+    t.mismatches = (unsigned long long *)alloc(2 * sizeof(unsigned long long));
+    ok = ok && seqs && t.send && t.recv && t.flags && t.mismatches;
+    int rc = RST_B200_OK;
+    if (!ok) rc = fail(RST_B200_ERR_CUDA, "self-test allocation failed");
+    else {
+        t.nan_words = t.mismatches + 1;
+        for (int r = 0; r < world; ++r) {
+            for (int p = 0; p < world; ++p) t.peers[r].mailbox[p] = boxes[p];
+            t.peers[r].seq_dev = seqs + r;
+            t.peers[r].timeout_cycles = (long long)(timeout_ms * (double)khz);
+        }
+        t.world = world; t.pay = pay; t.rounds = rounds; t.absent = absent_rank;
+        t.counts[0] = 8; t.counts[1] = pay / 2 > 0 ? pay / 2 : 1; t.counts[2] = pay;
+        void *args[] = {&t};
+        cudaError_t e = cudaLaunchCooperativeKernel((void *)p2p_selftest_kernel, dim3(world), dim3(256), args, 0, nullptr);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = fail(RST_B200_ERR_CUDA, std::string("p2p self-test: ") + cudaGetErrorString(e));
+        else {
+            unsigned long long h[2] = {0, 0};
+            std::vector<unsigned> hf(4 * world);
+            cudaMemcpy(h, t.mismatches, sizeof(h), cudaMemcpyDeviceToHost);
+            cudaMemcpy(hf.data(), t.flags, sizeof(unsigned) * 4 * world, cudaMemcpyDeviceToHost);
+            if (mismatches) *mismatches = (int64_t)h[0];
+            if (nan_words) *nan_words = (int64_t)h[1];
+            int tf = 0;
+            for (int r = 0; r < world; ++r) tf += (hf[4 * r + 2] & RST_FLAG_PEER_TIMEOUT) ? 1 : 0;
+            if (timeout_flags) *timeout_flags = tf;
+        }
+    }
+    for (void *q : owned) cudaFree(q);
+    return rc;
 }
 
 // handles: [world][handle_stride bytes] in rank order (own entry ignored)
@@ -1150,6 +1230,14 @@ extern "C" int rst_b200_p2p_open(rst_b200_solver *s, const void *handles, size_t
         TRY(dev_alloc(s, &d_seq, (size_t)1));
         CUDA_TRY(cudaMemset(d_seq, 0, sizeof(unsigned long long)));
         s->peers.seq_dev = d_seq;
+    }
+    {   // spin budget of the exchange (default 30 s: rank skew from lazy peer mapping, module load or a host-side regrid on
+        // one rank must not raise a spurious timeout); RST_B200_PEER_TIMEOUT_MS overrides it
+        const char *e = std::getenv("RST_B200_PEER_TIMEOUT_MS");
+        const double ms = e ? std::atof(e) : 30000.0;
+        int khz = 1965000;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, s->device);
+        s->peers.timeout_cycles = (long long)(ms * (double)khz);
     }
     s->p2p_enabled = true;
     P2pIface &I = s->iface;

@@ -99,6 +99,7 @@ SYMBOLS = {
     "rst_b200_set_allgather": (C.c_int, [_H, ALLGATHER_FN, C.c_void_p]),
     "rst_b200_p2p_get_handle": (C.c_int, [_H, C.c_void_p, C.c_size_t]),
     "rst_b200_p2p_open": (C.c_int, [_H, C.c_void_p, C.c_size_t]),
+    "rst_b200_p2p_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_i64_p, c_i64_p, c_int_p]),
     "rst_b200_dist_range": (C.c_int, [_H, c_i64_p, c_i64_p]),
     "rst_b200_factor_local": (C.c_int, [_H]),
     "rst_b200_factor_reduced": (C.c_int, [_H]),

@@ -44,7 +44,8 @@ struct Abd4Cfg {
     static constexpr int CT = (NC + 7) / 8;    // column tiles (last one may be half padding)
     static constexpr int NB = NV / 4;          // pivot blocks
     static constexpr int SH = NV / 4;          // tile distance between the M and the Q part (2 nv columns)
-    static constexpr int PITCH = 8 * CT + 4;   // pivot-row buffer pitch: conflict-free B-fragment reads
+    static constexpr int PITCH = 8 * CT + 4;   // pitch of the 4 raw pivot rows of a block: conflict-free B-fragment reads
+    static constexpr int PITCH_W = 8 * CT + 2; // pitch of the nv final pivot rows: the transposing U|E|F write-out reads columns
     static constexpr int PIV_STRIDE = 16;      // bytes of pivot-slot record per block row
     __host__ __device__ static constexpr int lt_off(int b) { return 4 * R2 * b - 8 * b * (b - 1); }
     static constexpr int LT = 4 * R2 * NB - 8 * NB * (NB - 1);
@@ -61,6 +62,21 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ unsigned lanes_below(int lane) { return (1u << lane) - 1u; }
+// predicated 16-byte shared-memory store (no branch, no reconvergence point)
+__device__ __forceinline__ void sts128_if(bool pred, double *p, double2 v) {
+    asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.b32 pp, %3, 0;\n\t@pp st.shared.v2.f64 [%0], {%1, %2};\n\t}"
+                 ::"r"((unsigned)__cvta_generic_to_shared(p)), "d"(v.x), "d"(v.y), "r"((int)pred) : "memory");
+}
+// reciprocal without the slow-path subroutine of __drcp_rn: MUFU.RCP64H seed (2^-23) + two Newton steps (~1 ulp).
+// Denormal / zero / non-finite pivots give inf / NaN and are reported through the zero-pivot flag by the caller.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 
 // part (0 = M, 1 = P, 2 = Q, 3 = padding) of the column pair a lane holds in column tile TC.  nv is a multiple of 4, so a
 // tile crosses at most one part boundary, in its middle: lanes with (lane & 3) < 2 hold the low half.
@@ -70,18 +86,28 @@ struct Abd4Tile {
     static constexpr bool SPLIT = LO != HI;
 };
 
+// shared memory of one warp of the factor kernel (dynamic: 4 warps need 46..90 KB)
+template <int NV, bool IDENT_B>
+struct Abd4Smem {
+    using Cf = Abd4Cfg<NV>;
+    static constexpr int STG = (IDENT_B ? 1 : 2) * NV * NV;   // doubles staged per block row
+    double pan[4 * Cf::R2];             // pivot-column panel [column plane][slot]; planes ordered 0, 2, 1, 3 (bank spread)
+    double lb[4 * Cf::R2 + 8];          // -Lt of the block (A fragments): columns (0,1) of every slot, then (+8: other banks) columns (2,3)
+    double pr[4 * 4];                   // pivot row of each of the block's 4 pivots (its own entry replaced by 1/pivot)
+    double xs[NV * Cf::PITCH_W];        // 4 raw pivot rows of a block (B fragments) / nv final pivot rows (U|E|F write-out)
+    double stage[2][STG];               // next block row(s), filled by cp.async
+    int pv[Cf::R2];                     // pivot index of each slot in the current block row
+};
+
 template <int NV, bool IDENT_B>
 __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigned *flags) {
     using Cf = Abd4Cfg<NV>;
     using Pk = AbdPack<NV>;
-    constexpr int R2 = Cf::R2, RT = Cf::RT, CT = Cf::CT, NB = Cf::NB, SH = Cf::SH, PITCH = Cf::PITCH;
+    using Sm = Abd4Smem<NV, IDENT_B>;
+    constexpr int R2 = Cf::R2, RT = Cf::RT, CT = Cf::CT, NB = Cf::NB, SH = Cf::SH, PITCH = Cf::PITCH, PITCH_W = Cf::PITCH_W;
     constexpr int BL = NV * NV;
-    constexpr int STG = IDENT_B ? BL : 2 * BL;   // doubles staged per block row
-    __shared__ __align__(16) double s_pan[4][R2 * 4];
-    __shared__ __align__(16) double s_lb[4][R2 * 4];
-    __shared__ __align__(16) double s_ub[4][4 * PITCH];
-    __shared__ __align__(16) double s_stage[4][2][STG];
-    __shared__ int s_pv[4][R2];
+    constexpr int NM = (Pk::UEF + 31) / 32;   // U|E|F doubles written per lane and block row
+    extern __shared__ __align__(16) unsigned char abd4_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, q = lane & 3;
     const bool hi = q >= 2;
@@ -89,12 +115,13 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
     if (slab >= L.nslabs) return;
     const int64_t g0 = slab * (int64_t)L.S;
     const int len = (int)((L.n - g0) < (int64_t)L.S ? (L.n - g0) : (int64_t)L.S);
-    double *pan = s_pan[warp], *lb = s_lb[warp], *ub = s_ub[warp];
-    int *pvs = s_pv[warp];
+    Sm &sm = reinterpret_cast<Sm *>(abd4_smem_raw)[warp];
+    double *pan = sm.pan, *lb = sm.lb, *xs = sm.xs, *pr = sm.pr;
+    int *pvs = sm.pv;
 
     auto stage = [&](int64_t g, int buf) {
         const char *srcA = reinterpret_cast<const char *>(L.A + g * (int64_t)BL);
-        char *dst = reinterpret_cast<char *>(s_stage[warp][buf]);
+        char *dst = reinterpret_cast<char *>(sm.stage[buf]);
         for (int c = lane; c < BL / 2; c += 32) cp_async16(dst + c * 16, srcA + c * 16);
         if constexpr (!IDENT_B) {
             const char *srcB = reinterpret_cast<const char *>(L.B + g * (int64_t)BL);
@@ -104,10 +131,32 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
     };
     if (len > 1) stage(g0 + 1, 1);
 
+    // U|E|F write-out map: output double i = lane + 32 m of a block row comes from pivot row k(i), panel column col(i);
+    // byte offsets into xs (rows by pivot index), two per register
+    unsigned wmap[(NM + 1) / 2];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+        const int i = lane + 32 * m;
+        int k = 0, col = 0;
+        if (i < Pk::TRI) {
+            int c = 0;
+            while ((c + 1) * (c + 2) / 2 <= i) ++c;
+            k = i - c * (c + 1) / 2;
+            col = c;
+        } else if (i < Pk::UEF) {
+            const int j = i - Pk::TRI;
+            k = j % NV;
+            col = NV + j / NV;
+        }
+        const unsigned off = (unsigned)((k * PITCH_W + col) * 8);
+        if (m % 2 == 0) wmap[m / 2] = off; else wmap[m / 2] |= off << 16;
+    }
+
     // panel in accumulator layout: X[T][TC] = (row 8T + gid, columns 8TC + 2q, 8TC + 2q + 1)
     double2 X[RT][CT];
     // carry rows of the slab start: slots 0..nv-1 = block row g0 as [ . | P = A | Q = B ]
     unsigned carrymask = (1u << NV) - 1u;
+    unsigned bad = 0u;
 #pragma unroll
     for (int T = 0; T < RT; ++T) {
         const int slot = 8 * T + gid;
@@ -132,7 +181,7 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
         const int64_t g = g0 + i;
         cp_async_wait_all();
         __syncwarp();
-        const double *stA = s_stage[warp][i & 1];
+        const double *stA = sm.stage[i & 1];
         // ---- carry rows: M <- Q, Q <- 0; free slots: next block row [M = A | 0 | Q = B] ---------------------------
         const unsigned freemask = ~carrymask & Cf::ALL;
 #pragma unroll
@@ -140,31 +189,41 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
             const int slot = 8 * T + gid;
             const bool fr = (freemask >> slot) & 1u;
             const int t = __popc(freemask & lanes_below(slot));
-            static_for<0, CT>([&](auto tc) {
-                constexpr int TC = decltype(tc)::value;
-                using Tl = Abd4Tile<NV, TC>;
-                const int part = (Tl::SPLIT && hi) ? Tl::HI : Tl::LO;
-                const int idx = 8 * TC + 2 * q - part * NV;
-                double2 nv_ = make_double2(0.0, 0.0);   // value of a new row
-                double2 cv = make_double2(0.0, 0.0);    // value of a carry row
-                auto for_part = [&](int pt) {
-                    if (pt == 0) {
-                        if (fr) nv_ = *reinterpret_cast<const double2 *>(stA + t * NV + idx);
-                        if constexpr (TC + SH < CT) cv = X[T][TC + SH];
-                    } else if (pt == 1) {
-                        cv = X[T][TC];
-                    } else if (pt == 2) {
-                        if constexpr (IDENT_B) nv_ = make_double2(idx == t ? 1.0 : 0.0, idx + 1 == t ? 1.0 : 0.0);
-                        else if (fr) nv_ = *reinterpret_cast<const double2 *>(stA + BL + t * NV + idx);
+            if (fr) {
+                static_for<0, CT>([&](auto tc) {
+                    constexpr int TC = decltype(tc)::value;
+                    using Tl = Abd4Tile<NV, TC>;
+                    const int part = (Tl::SPLIT && hi) ? Tl::HI : Tl::LO;
+                    const int idx = 8 * TC + 2 * q - part * NV;
+                    double2 v = make_double2(0.0, 0.0);
+                    if (Tl::LO == 0 || Tl::HI == 0) {
+                        if (part == 0) v = *reinterpret_cast<const double2 *>(stA + t * NV + idx);
                     }
-                };
-                if constexpr (Tl::SPLIT) {
-                    if (!hi) for_part(Tl::LO); else for_part(Tl::HI);
-                } else {
-                    for_part(Tl::LO);
-                }
-                X[T][TC] = fr ? nv_ : cv;
-            });
+                    if (Tl::LO == 2 || Tl::HI == 2) {
+                        if (part == 2) {
+                            if constexpr (IDENT_B) v = make_double2(idx == t ? 1.0 : 0.0, idx + 1 == t ? 1.0 : 0.0);
+                            else v = *reinterpret_cast<const double2 *>(stA + BL + t * NV + idx);
+                        }
+                    }
+                    X[T][TC] = v;
+                });
+            } else {
+                static_for<0, CT>([&](auto tc) {
+                    constexpr int TC = decltype(tc)::value;
+                    using Tl = Abd4Tile<NV, TC>;
+                    if constexpr (!Tl::SPLIT) {
+                        if constexpr (Tl::LO == 0) X[T][TC] = X[T][TC + SH];
+                        else if constexpr (Tl::LO != 1) X[T][TC] = make_double2(0.0, 0.0);
+                    } else {
+                        // low half / high half of the tile belong to different parts
+                        double2 lo_v = X[T][TC], hi_v = X[T][TC];
+                        if constexpr (Tl::LO == 0) { if constexpr (TC + SH < CT) lo_v = X[T][TC + SH]; }
+                        else if constexpr (Tl::LO != 1) lo_v = make_double2(0.0, 0.0);
+                        if constexpr (Tl::HI != 1) hi_v = make_double2(0.0, 0.0);
+                        X[T][TC] = hi ? hi_v : lo_v;
+                    }
+                });
+            }
         }
         __syncwarp();                       // every lane has read its staged rows: the other buffer may be refilled
         if (i + 1 < len) stage(g + 1, (i + 1) & 1);
@@ -180,55 +239,68 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
             const bool blk_hi = ((4 * b) % 8) != 0;
             // (a) gather the 2nv x 4 pivot-column panel: one row per lane
 #pragma unroll
-            for (int T = 0; T < RT; ++T)
-                if (hi == blk_hi) *reinterpret_cast<double2 *>(pan + (8 * T + gid) * 4 + 2 * (q & 1)) = X[T][TCB];
+            for (int T = 0; T < RT; ++T) {
+                if (hi == blk_hi) {
+                    pan[(q & 1) * R2 + 8 * T + gid] = X[T][TCB].x;          // column 2 (q & 1)     -> plane (q & 1)
+                    pan[(2 + (q & 1)) * R2 + 8 * T + gid] = X[T][TCB].y;    // column 2 (q & 1) + 1 -> plane 2 + (q & 1)
+                }
+            }
             __syncwarp();
             double a[4];
             {
                 const int row = lane < R2 ? lane : 0;
-                const double2 v0 = *reinterpret_cast<const double2 *>(pan + row * 4);
-                const double2 v1 = *reinterpret_cast<const double2 *>(pan + row * 4 + 2);
-                a[0] = v0.x; a[1] = v0.y; a[2] = v1.x; a[3] = v1.y;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a[j] = pan[((j >> 1) | ((j & 1) << 1)) * R2 + row];
             }
             // (b) 4 pivots with partial pivoting over the candidate slots
             const unsigned cand0 = cand_mask;
             bool cand = (lane < R2) && ((cand_mask >> lane) & 1u);
             const bool cand_at_start = cand;
-            int mypiv = -1;                 // 0..3: my slot became pivot `mypiv` of this block
+            int mypiv = 4;                  // 0..3: my slot became pivot `mypiv` of this block
             int ps[4];
+            double n10 = 0.0, n20 = 0.0, n21 = 0.0, n30 = 0.0, n31 = 0.0, n32 = 0.0;   // strict lower triangle of the block
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
-                const int p = group_argmax_redux<32>(a[ii], cand, 0, RST_FULL_MASK);
+                // arg-max of |a[ii]| over the candidates: ONE 32-bit REDUX on (high word of |a| with its low 5 bits replaced
+                // by 31 - lane): ties and values equal in their leading 15 mantissa bits resolve to the lowest slot
+                const unsigned hw = (unsigned)__double2hiint(a[ii]) & 0x7fffffffu;
+                const unsigned key = cand ? (((hw & ~31u) | (unsigned)(31 - lane)) + 1u) : 0u;
+                const double myr = fast_rcp(a[ii]);        // every lane inverts its own entry while the REDUX is in flight
+                const unsigned mx = __reduce_max_sync(RST_FULL_MASK, key);
+                const int p = 31 - (int)((mx - 1u) & 31u);
                 ps[ii] = p;
-                double ap[4];
-#pragma unroll
-                for (int j = ii; j < 4; ++j) ap[j] = __shfl_sync(RST_FULL_MASK, a[j], p);
-                if (!(fabs(ap[ii]) > 0.0) && lane == 0) atomicOr(flags, RST_FLAG_ZERO_PIVOT);
-                const double rinv = __drcp_rn(ap[ii]);
-                const bool is_piv = lane == p;
-                if (cand && !is_piv) {
-                    const double l = a[ii] * rinv;
-                    a[ii] = l;
-#pragma unroll
-                    for (int j = ii + 1; j < 4; ++j) a[j] = fma(-l, ap[j], a[j]);
+                // the pivot lane publishes its row (multipliers of the earlier pivots | 1/pivot | entries to the right) through
+                // shared memory: 4 wavefronts instead of 8-10 shuffles per pivot, and the triangle of (c) comes for free
+                if (lane == p) {
+                    *reinterpret_cast<double2 *>(pr + 4 * ii) = make_double2(ii == 0 ? myr : a[0], ii == 1 ? myr : a[1]);
+                    *reinterpret_cast<double2 *>(pr + 4 * ii + 2) = make_double2(ii == 2 ? myr : a[2], ii == 3 ? myr : a[3]);
                 }
+                __syncwarp();
+                double ap[4];
+                {
+                    const double2 r0 = *reinterpret_cast<const double2 *>(pr + 4 * ii);
+                    const double2 r1 = *reinterpret_cast<const double2 *>(pr + 4 * ii + 2);
+                    ap[0] = r0.x; ap[1] = r0.y; ap[2] = r1.x; ap[3] = r1.y;
+                }
+                const double rinv = ap[ii];
+                if (ii == 1) { n10 = ap[0]; }
+                if (ii == 2) { n20 = ap[0]; n21 = ap[1]; }
+                if (ii == 3) { n30 = ap[0]; n31 = ap[1]; n32 = ap[2]; }
+                bad |= (mx <= 32u || mx > 0x7ff00000u) ? 1u : 0u;   // zero / denormal or non-finite pivot
+                const bool is_piv = lane == p;
+                const bool upd = cand && !is_piv;
+                const double l = upd ? a[ii] * rinv : 0.0;
+                if (upd) a[ii] = l;
+#pragma unroll
+                for (int j = ii + 1; j < 4; ++j) a[j] = fma(-l, ap[j], a[j]);
                 if (is_piv) { mypiv = ii; pv = 4 * b + ii; cand = false; }
                 cand_mask &= ~(1u << p);
             }
             pword[b] = (unsigned)ps[0] | ((unsigned)ps[1] << 8) | ((unsigned)ps[2] << 16) | ((unsigned)ps[3] << 24);
             // multipliers of my slot: candidates keep all four, pivot ii keeps those of the earlier pivots, others none
-            double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
-            if (cand_at_start) {
-                const int lim = mypiv < 0 ? 4 : mypiv;
-                l0 = lim > 0 ? a[0] : 0.0; l1 = lim > 1 ? a[1] : 0.0; l2 = lim > 2 ? a[2] : 0.0; l3 = lim > 3 ? a[3] : 0.0;
-            }
+            const int lim = cand_at_start ? mypiv : 0;
+            const double l0 = lim > 0 ? a[0] : 0.0, l1 = lim > 1 ? a[1] : 0.0, l2 = lim > 2 ? a[2] : 0.0, l3 = lim > 3 ? a[3] : 0.0;
             // (c) inverse of the block's unit lower triangle (strict part n_ij = multiplier of pivot row i at pivot j)
-            const double n10 = __shfl_sync(RST_FULL_MASK, l0, ps[1]);
-            const double n20 = __shfl_sync(RST_FULL_MASK, l0, ps[2]);
-            const double n21 = __shfl_sync(RST_FULL_MASK, l1, ps[2]);
-            const double n30 = __shfl_sync(RST_FULL_MASK, l0, ps[3]);
-            const double n31 = __shfl_sync(RST_FULL_MASK, l1, ps[3]);
-            const double n32 = __shfl_sync(RST_FULL_MASK, l2, ps[3]);
             const double i10 = -n10;
             const double i21 = -n21, i20 = -fma(n21, i10, n20);
             const double i32 = -n32, i31 = -fma(n32, i21, n31), i30 = -fma(n32, i20, fma(n31, i10, n30));
@@ -239,8 +311,8 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
             const double t0 = fma(l3, i30, fma(l2, i20, fma(l1, i10, l0)));
             // (d) Lt: shared memory (A fragments) + HBM (forward sweep)
             if (lane < R2) {
-                *reinterpret_cast<double2 *>(lb + lane * 4) = make_double2(-t0, -t1);
-                *reinterpret_cast<double2 *>(lb + lane * 4 + 2) = make_double2(-t2, -t3);
+                *reinterpret_cast<double2 *>(lb + lane * 2) = make_double2(-t0, -t1);
+                *reinterpret_cast<double2 *>(lb + 2 * R2 + 8 + lane * 2) = make_double2(-t2, -t3);
                 if (b == NB - 1) pvs[lane] = pv;
             }
             if (cand_at_start) {
@@ -248,32 +320,26 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
                 double *dst = lt_g + Cf::lt_off(b) + __popc(cand0 & lanes_below(lane));
                 st_cs(dst, t0); st_cs(dst + ncand, t1); st_cs(dst + 2 * ncand, t2); st_cs(dst + 3 * ncand, t3);
             }
-            // (e) raw pivot rows -> shared memory (B fragments)
+            // (e) raw rows of the block's 4 pivots -> shared memory (B fragments); which pivot my slot is comes from its lane
 #pragma unroll
             for (int T = 0; T < RT; ++T) {
-                const int slot = 8 * T + gid;
-                int which = -1;
+                const int which = __shfl_sync(RST_FULL_MASK, mypiv, 8 * T + gid);
 #pragma unroll
-                for (int ii = 0; ii < 4; ++ii) which = (slot == ps[ii]) ? ii : which;
-                if (which >= 0) {
-#pragma unroll
-                    for (int TC = TCB; TC < CT; ++TC)
-                        *reinterpret_cast<double2 *>(ub + which * PITCH + 8 * TC + 2 * q) = X[T][TC];
-                }
+                for (int TC = TCB; TC < CT; ++TC) sts128_if(which < 4, xs + which * PITCH + 8 * TC + 2 * q, X[T][TC]);
             }
             __syncwarp();
-            // (f) + (g): X <- X - Lt * X[pivot rows] on the FP64 tensor cores
+            // (f): X <- X - Lt * X[pivot rows] on the FP64 tensor cores
             double af[RT];
 #pragma unroll
-            for (int T = 0; T < RT; ++T) af[T] = lb[32 * T + lane];
+            for (int T = 0; T < RT; ++T) af[T] = lb[(q >> 1) * (2 * R2 + 8) + (8 * T + gid) * 2 + (q & 1)];
 #pragma unroll
             for (int TC = TCB; TC < CT; ++TC) {
-                const double bf = ub[q * PITCH + 8 * TC + gid];
+                const double bf = xs[q * PITCH + 8 * TC + gid];
 #pragma unroll
                 for (int T = 0; T < RT; ++T) dmma_m8n8k4(X[T][TC], af[T], bf);
             }
+            __syncwarp();   // xs / lb / pan are rewritten by the next block (or the write-out below)
         }
-        __syncwarp();   // pvs visible
         // ---- pivot rows -> U | E | F (layout of abd.cuh), pivot slots -> piv --------------------------------------
         if (lane < NB) {
             unsigned w = pword[0];
@@ -281,32 +347,27 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
             for (int b = 1; b < NB; ++b) w = (lane == b) ? pword[b] : w;
             reinterpret_cast<unsigned *>(L.piv + g * (int64_t)Cf::PIV_STRIDE)[lane] = w;
         }
-        double *uef = L.UEF + g * (int64_t)Pk::UEF;
 #pragma unroll
-        for (int T = 0; T < RT; ++T) {
+        for (int T = 0; T < RT; ++T) {      // final pivot rows, ordered by pivot index
             const int k = pvs[8 * T + gid];
-            if (k >= 0) {
-                static_for<0, CT>([&](auto tc) {
-                    constexpr int TC = decltype(tc)::value;
-                    using Tl = Abd4Tile<NV, TC>;
-                    const int part = (Tl::SPLIT && hi) ? Tl::HI : Tl::LO;
-                    const int idx = 8 * TC + 2 * q - part * NV;
-                    const double2 v = X[T][TC];
-                    if (part == 0) {
-                        if (idx >= k) st_cs(uef + Pk::u_off(idx) + k, v.x);
-                        if (idx + 1 >= k) st_cs(uef + Pk::u_off(idx + 1) + k, v.y);
-                    } else if (part == 1) {
-                        st_cs(uef + Pk::TRI + idx * NV + k, v.x);
-                        st_cs(uef + Pk::TRI + (idx + 1) * NV + k, v.y);
-                    } else if (part == 2) {
-                        st_cs(uef + Pk::TRI + BL + idx * NV + k, v.x);
-                        st_cs(uef + Pk::TRI + BL + (idx + 1) * NV + k, v.y);
-                    }
-                });
+#pragma unroll
+            for (int TC = 0; TC < CT; ++TC) sts128_if(k >= 0, xs + k * PITCH_W + 8 * TC + 2 * q, X[T][TC]);
+        }
+        __syncwarp();
+        {   // coalesced write-out: lane handles doubles lane, lane + 32, ... of the record
+            double *uef = L.UEF + g * (int64_t)Pk::UEF + lane;
+            const char *xb = reinterpret_cast<const char *>(xs);
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                const unsigned off = (m % 2 == 0) ? (wmap[m / 2] & 0xffffu) : (wmap[m / 2] >> 16);
+                const double v = *reinterpret_cast<const double *>(xb + off);
+                if (32 * m + 31 < Pk::UEF || lane + 32 * m < Pk::UEF) st_cs(uef + 32 * m, v);
             }
         }
         carrymask = cand_mask;
+        // (the next block row's first __syncwarp orders these xs reads before its writes)
     }
+    if (bad && lane == 0) atomicOr(flags, RST_FLAG_ZERO_PIVOT);
     // ---- condensed row of the slab: A_next = P part, B_next = Q part of the surviving slots -------------------------
 #pragma unroll
     for (int T = 0; T < RT; ++T) {

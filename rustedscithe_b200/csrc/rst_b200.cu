@@ -148,8 +148,16 @@ struct SolverImpl {
         if constexpr (HAS_V4) {
             if (use_v4()) {
                 const unsigned blocks = (unsigned)((L.nslabs + 3) / 4);
-                if (ident_b) abd_factor4_kernel<NV, true><<<blocks, 128, 0, st>>>(L, flags);
-                else abd_factor4_kernel<NV, false><<<blocks, 128, 0, st>>>(L, flags);
+                // > 48 KB of dynamic shared memory: opt in on every launch (the attribute is per device and per loaded module)
+                if (ident_b) {
+                    constexpr int smem = 4 * (int)sizeof(Abd4Smem<NV, true>);
+                    cudaFuncSetAttribute(abd_factor4_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    abd_factor4_kernel<NV, true><<<blocks, 128, smem, st>>>(L, flags);
+                } else {
+                    constexpr int smem = 4 * (int)sizeof(Abd4Smem<NV, false>);
+                    cudaFuncSetAttribute(abd_factor4_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    abd_factor4_kernel<NV, false><<<blocks, 128, smem, st>>>(L, flags);
+                }
                 return;
             }
         }

@@ -178,6 +178,32 @@ int rst_b200_newton_frozen(rst_b200_solver *s, const rst_b200_frozen_opts *opts,
 /* DirectLinearSolver::solve_in_place (solver_traits.rs:3-14): rhs[N*nv] in the reference's row order,
  * overwritten with the solution in the reference's reduced column order. Needs rst_b200_factor. */
 int rst_b200_solve_in_place(rst_b200_solver *s, double *rhs, size_t len);
+/* LinearSolverConfig (src/somelinalg/banded/solver_policy.rs:10-89): policy / fallback / guarded-refinement budget of the
+ * DirectLinearSolver drop-ins.  Numbering = declaration order of the reference's enums. */
+enum rst_b200_linear_solver_policy {            /* LinearSolverPolicy, solver_policy.rs:10-17 */
+    RST_B200_LS_AUTO = 0,
+    RST_B200_LS_FORCE_BLOCK_TRIDIAGONAL = 1,
+    RST_B200_LS_FORCE_BLOCK_TRIDIAGONAL_CONSISTENT = 2,
+    RST_B200_LS_FORCE_BANDED = 3,
+    RST_B200_LS_FORCE_GENERAL_BANDED_PARTIAL_PIVOT = 4,   /* CPU diagnostic back-end: RST_B200_ERR_UNSUPPORTED */
+    RST_B200_LS_FORCE_FAER_SPARSE = 5                     /* CPU back-end (faer): RST_B200_ERR_UNSUPPORTED */
+};
+enum rst_b200_fallback_policy {                 /* FallbackPolicy, solver_policy.rs:19-23 */
+    RST_B200_FALLBACK_NEVER = 0,
+    RST_B200_FALLBACK_TO_FAER_SPARSE = 1        /* accepted and remembered; a zero pivot is reported, never retried on a CPU */
+};
+/* Defaults mirror LinearSolverConfig::default(): Auto, ToFaerSparse, 0 refinement steps.  Auto / ForceBanded /
+ * ForceBlockTridiagonal* all select the pivoted condensation solver (it handles both matrix classes, including the node
+ * blocks the reference's block solver rejects).  iterative_refinement_steps > 0 makes rst_b200_solve_in_place /
+ * _solve_multiple_in_place run the guarded refinement below with tol = 1e-12 (linear_solver.rs:84-101). */
+int rst_b200_set_linear_solver_config(rst_b200_solver *s, int policy, int fallback, int iterative_refinement_steps);
+int rst_b200_get_linear_solver_config(const rst_b200_solver *s, int *policy, int *fallback, int *iterative_refinement_steps);
+/* solve_in_place_with_refinement (lapack_style_banded.rs:1227-1298): solve, then at most max_iters guarded steps of
+ * iterative refinement x' = x + J^-1 (b - J x); a step is kept only while max|b - J x| / max(max|b|, 1) decreases, the loop
+ * ends once that ratio is below tol.  The residual is formed on the device with the blocks that were factored.
+ * accepted_steps / final_rel_residual may be NULL. */
+int rst_b200_solve_in_place_with_refinement(rst_b200_solver *s, double *rhs, size_t len, int max_iters, double tol,
+                                            int *accepted_steps, double *final_rel_residual);
 /* solve_multiple_in_place: column-major, leading dimension ldb >= n */
 int rst_b200_solve_multiple_in_place(rst_b200_solver *s, double *rhs, size_t nrhs, size_t ldb);
 /* sparse/banded structure of the value stream (BandedJacobianStructure, codegen_runtime_api.rs:414-421):

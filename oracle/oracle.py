@@ -247,6 +247,32 @@ class OracleBVP:
         ab, ipiv = dgb_factor(self.n, kl, ku, banded_to_ab(self.n, kl, ku, banded))
         return dgb_solve(self.n, kl, ku, ab, ipiv, rhs)
 
+    def solve_banded_with_refinement(self, values, rhs, max_iters=2, tol=1e-14):
+        """solve_in_place_with_refinement (lapack_style_banded.rs:1227-1298) with the banded matvec of the same matrix:
+        a refinement step is accepted only while max|b - A x| / max(max|b|, 1) decreases.  Returns (x, accepted)."""
+        _, _, _, _, kl, ku = self.structure()
+        banded = self.banded(values)
+        ab, ipiv = dgb_factor(self.n, kl, ku, banded_to_ab(self.n, kl, ku, banded))
+        b = _f64(rhs).copy()
+        x = dgb_solve(self.n, kl, ku, ab, ipiv, b)
+        b_norm = max(float(np.max(np.abs(b))), 1.0)
+        current_rr = np.inf
+        accepted = 0
+        for _ in range(max_iters):
+            residual = b - banded_matvec(self.n, kl, ku, banded, x)
+            rr = float(np.max(np.abs(residual))) / b_norm
+            if not np.isfinite(rr) or rr < tol:
+                break
+            if not np.isfinite(current_rr):
+                current_rr = rr
+            x_trial = x + dgb_solve(self.n, kl, ku, ab, ipiv, residual)
+            trial_rr = float(np.max(np.abs(b - banded_matvec(self.n, kl, ku, banded, x_trial)))) / b_norm
+            if not np.isfinite(trial_rr) or trial_rr >= min(rr, current_rr):
+                break
+            x, current_rr = x_trial, trial_rr
+            accepted += 1
+        return x, accepted
+
     # -- Newton ------------------------------------------------------------------------------
     def newton(self, y0, lo, hi, rtol, abs_tol=1e-6, max_iterations=25, max_jac=3, max_damp_iter=5,
                damp_factor=0.5, refactor_per_solve=True) -> NewtonResult:

@@ -268,4 +268,60 @@ __global__ void __launch_bounds__(32) assemble_j_staged_kernel(AsmArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Residual-only assembly with shared-memory staged state and residual (nv <= 16).
+// assemble_kernel<P, false> reads Y_j / Y_{j+1} and writes r_j with a lane stride of nv doubles: every 16-byte access
+// of a warp touches 32 different lines (measured 0.45 of the HBM roofline at nv = 12, profiles/r01_c_summary.md; the
+// kernel runs twice per damped Newton iteration).  Here a CTA owns 128 consecutive intervals: their 129 nodes come in
+// with fully coalesced loads into an odd-pitch tile (each lane then reads its two nodes conflict-free), the residual
+// rows leave through a second tile with fully coalesced stores.
+// ------------------------------------------------------------------------------------------------
+template <class P, bool TRAPEZOID>
+__global__ void __launch_bounds__(128) assemble_f_staged_kernel(AsmArgs a) {
+    constexpr int NV = P::NV, PITCH = NV | 1, TJ = 128;
+    __shared__ double ysm[(TJ + 1) * PITCH];
+    __shared__ double rsm[TJ * PITCH];
+    const int tid = threadIdx.x;
+    const int64_t j0 = (int64_t)blockIdx.x * TJ;
+    const int nj = (int)((a.n - j0) < TJ ? (a.n - j0) : TJ);       // intervals of this CTA
+    {
+        const double *src = a.Y + j0 * NV;
+        const int total = (nj + 1) * NV;
+        for (int idx = tid; idx < total; idx += TJ) ysm[(idx / NV) * PITCH + (idx % NV)] = src[idx];
+    }
+    __syncthreads();
+    if (tid < nj) {
+        const int64_t j = j0 + tid;
+        double y0[NV], y1[NV], f0[NV];
+#pragma unroll
+        for (int c = 0; c < NV; ++c) { y0[c] = ysm[tid * PITCH + c]; y1[c] = ysm[(tid + 1) * PITCH + c]; }
+        double t, t1, h;
+        if (a.mesh) {
+            t = a.mesh[j];
+            t1 = a.mesh[j + 1];
+            h = t1 - t;
+        } else {
+            t = a.t0 + (double)(j + a.j_offset) * a.h;
+            t1 = a.t0 + (double)(j + a.j_offset + 1) * a.h;
+            h = a.h;
+        }
+        P::eval_f(t, y0, a.params, f0);
+        if constexpr (!TRAPEZOID) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) rsm[tid * PITCH + i] = y1[i] - y0[i] - h * f0[i];
+        } else {
+            double f1[NV];
+            P::eval_f(a.trap_time ? t1 : t, y1, a.params, f1);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) rsm[tid * PITCH + i] = y1[i] - y0[i] - 0.5 * h * (f0[i] + f1[i]);
+        }
+    }
+    __syncthreads();
+    {
+        double *dst = a.F + j0 * NV;
+        const int total = nj * NV;
+        for (int idx = tid; idx < total; idx += TJ) st_cs(dst + idx, rsm[(idx / NV) * PITCH + (idx % NV)]);
+    }
+}
+
 }  // namespace rst

@@ -289,6 +289,42 @@ __global__ void __launch_bounds__(128) block_residual_kernel(const double *__res
     out[idx] = s;
 }
 
+// run-time block size (wide blocks): one thread per residual row
+__global__ void __launch_bounds__(128) block_residual_generic_kernel(const double *__restrict__ A, const double *__restrict__ B,
+                                                                     const double *__restrict__ X, const double *__restrict__ rhs,
+                                                                     double *__restrict__ out, int64_t n, int nv) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * nv) return;
+    const int64_t j = idx / nv;
+    const int i = (int)(idx - j * nv);
+    const double *a = A + (j * nv + i) * (int64_t)nv;
+    double s = rhs[idx];
+    for (int c = 0; c < nv; ++c) s = fma(-a[c], X[j * nv + c], s);
+    if (B) {
+        const double *b = B + (j * nv + i) * (int64_t)nv;
+        for (int c = 0; c < nv; ++c) s = fma(-b[c], X[(j + 1) * nv + c], s);
+    } else {
+        s -= X[(j + 1) * nv + i];
+    }
+    out[idx] = s;
+}
+
+// max |v| as the bit pattern of a non-negative double (orders like an unsigned integer); NaN / inf map to all ones
+__global__ void __launch_bounds__(256) absmax_kernel(const double *__restrict__ v, int64_t total, unsigned long long *out) {
+    unsigned long long m = 0ull;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const double x = fabs(v[idx]);
+        const unsigned long long b = (x == x && x < 1.0e308 * 10.0) ? (unsigned long long)__double_as_longlong(x) : ~0ull;
+        m = b > m ? b : m;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(RST_FULL_MASK, m, off);
+        m = o > m ? o : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 __global__ void __launch_bounds__(256) axpy_kernel(double *__restrict__ x, const double *__restrict__ d, double alpha,
                                                    int64_t total) {
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;

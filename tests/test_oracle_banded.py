@@ -177,3 +177,28 @@ def test_matches_lapack_dgbtrf(seed, shape):
     assert np.max(np.abs(x - xl)) <= 1e-9 * max(1.0, np.max(np.abs(xl)))
     mine = ab.reshape(n, ldab).T
     assert np.allclose(mine, lu, rtol=1e-9, atol=1e-12)
+
+
+def test_guarded_refinement_restatement_never_increases_the_residual():
+    """solve_in_place_with_refinement (lapack_style_banded.rs:1227-1298) as restated in oracle.OracleBVP: on a BVP system
+    the accepted steps can only lower max|b - A x| / max(max|b|, 1); with tol above the first residual nothing is accepted
+    (the reference's early exit, :1264-1266)."""
+    from rustedscithe_b200 import problems
+    spec = problems.get("combustion6")
+    n = 400
+    o = orc.OracleBVP("combustion6", n, spec.bc_list(), t0=spec.t0, t_end=spec.t_end)
+    rng = np.random.default_rng(3)
+    y = spec.guess(n) * (1.0 + 0.01 * rng.standard_normal(o.n))
+    vals, rhs = o.jacobian_values(y), o.residual(y)
+    banded = o.banded(vals)
+    _, _, _, _, kl, ku = o.structure()
+
+    def rr(x):
+        return np.max(np.abs(rhs - orc.banded_matvec(o.n, kl, ku, banded, x))) / max(np.max(np.abs(rhs)), 1.0)
+
+    x0 = o.solve_banded(vals, rhs)
+    x, accepted = o.solve_banded_with_refinement(vals, rhs, 3, 1e-30)
+    assert 0 <= accepted <= 3
+    assert rr(x) <= rr(x0)
+    x_loose, acc_loose = o.solve_banded_with_refinement(vals, rhs, 3, 1.0)
+    assert acc_loose == 0 and np.array_equal(x_loose, x0)

@@ -445,6 +445,10 @@ static int dev_alloc(H *s, T **p, size_t count) {
 
 static int default_slab(int64_t n, int requested) {
     if (requested >= 2) return requested;
+    if (const char *e = std::getenv("RST_B200_SLAB_ALL")) {   // experiments: one slab length for every level
+        const int v = std::atoi(e);
+        if (v >= 2) return v;
+    }
     // measured at nv = 12, 1e6 rows (solve ms): S = 8 1.090, 12 1.065, 16 1.049, 32 1.078, 64 1.107 -- longer slabs mean fewer
     // levels but a longer dependent chain per warp; nv = 64: 16 beats 32 as well
     if (n >= (1 << 12)) return 16;

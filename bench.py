@@ -470,7 +470,7 @@ def run_workload(args, workload, rank, world, local_rank, primary):
         # ---- per-phase kernel timings for the roofline (same stream, CUDA events, L2 flushed before every launch) ------
         phases = {}
         regrid_ms = None
-        if world == 1:
+        if world == 1 or not args.nccl_exchange:   # N > 1: every rank runs the same phases (the exchanges are inside factor / solve)
             flush_buf = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
 
             def time_phase(fn, reps):
@@ -493,7 +493,7 @@ def run_workload(args, workload, rank, world, local_rank, primary):
             solver.eval_jacobian(0)
             phases["factor"] = time_phase(lambda: solver.factor(), reps)
             phases["solve"] = time_phase(lambda: solver.solve(), reps)
-            if primary:
+            if primary and world == 1:
                 # adaptive-grid hand-off on the current state (marks + scan + refined mesh + interpolated state, all on the device)
                 regrid_ms = time_phase(lambda: solver.new_grid("Pearson", (1e-3, 1.4), fetch=False), 3)
             del flush_buf

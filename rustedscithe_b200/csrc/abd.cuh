@@ -284,15 +284,15 @@ __global__ void __launch_bounds__(128) abd_forward_kernel(AbdLevel L) {
 // ------------------------------------------------------------------------------------------------
 // solve, backward sweep of one level: recover the interior nodes of every slab from its end nodes
 // ------------------------------------------------------------------------------------------------
+// body for one warp: `warp_index` counts warps over the level (32 / G slabs each)
 template <int NV>
-__global__ void __launch_bounds__(128) abd_backward_kernel(AbdLevel L) {
+__device__ __forceinline__ void abd_backward_warp(const AbdLevel &L, int64_t warp_index, int lane) {
     using Pk = AbdPack<NV>;
     constexpr int G = next_pow2(NV);
     constexpr int GPW = 32 / G;
-    const int lane = threadIdx.x & 31;
     const int k = lane & (G - 1);
     const int gw = lane / G;
-    const int64_t slab = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + gw;
+    const int64_t slab = warp_index * GPW + gw;
     const bool slab_ok = slab < L.nslabs;
     const bool k_ok = slab_ok && k < NV;
     const int64_t g0 = slab * (int64_t)L.S;
@@ -351,6 +351,11 @@ __global__ void __launch_bounds__(128) abd_backward_kernel(AbdLevel L) {
     }
 }
 
+template <int NV>
+__global__ void __launch_bounds__(128) abd_backward_kernel(AbdLevel L) {
+    abd_backward_warp<NV>(L, (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), threadIdx.x & 31);
+}
+
 // ------------------------------------------------------------------------------------------------
 // top of the recursion: the single remaining block row  C Z0 + D Z1 = g  closed with the boundary
 // conditions (pinned components have zero correction): an nv x nv dense system in the free components
@@ -358,12 +363,19 @@ __global__ void __launch_bounds__(128) abd_backward_kernel(AbdLevel L) {
 // with partial pivoting in shared memory.
 // ------------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(32) abd_top_solve_kernel(const double *C, const double *D, const double *g,
-                                                           double *Z /* [2][nv] */, unsigned long long left_mask,
-                                                           unsigned long long right_mask, unsigned *flags) {
-    __shared__ double K[NV][NV + 1];
-    __shared__ int colmap[NV];
-    const int lane = threadIdx.x;
+struct AbdTopSmem {
+    int colmap[NV];
+};
+
+// one warp, lane = row of the nv x nv closure system, the row lives in registers: pivot search with one REDUX per column
+// (rows never move; a retired row simply stops being a candidate), pivot row broadcast by shuffles, substitution by
+// shuffles.  (The first version kept K in shared memory and let lane 0 substitute: 17 us per linear solve at nv = 12.)
+template <int NV>
+__device__ __forceinline__ void abd_top_solve_warp(AbdTopSmem<NV> &sm, const double *C, const double *D, const double *g,
+                                                   double *Z /* [2][nv] */, unsigned long long left_mask,
+                                                   unsigned long long right_mask, unsigned *flags, int lane) {
+    static_assert(NV <= 32, "one row per lane");
+    int *colmap = sm.colmap;
     if (lane == 0) {
         int nc = 0;
         for (int c = 0; c < NV; ++c)
@@ -373,47 +385,61 @@ __global__ void __launch_bounds__(32) abd_top_solve_kernel(const double *C, cons
         if (nc != NV) atomicOr(flags, RST_FLAG_ZERO_PIVOT);
     }
     __syncwarp();
-    for (int idx = lane; idx < NV * NV; idx += 32) {
-        const int row = idx / NV, cc = idx % NV;
-        const int cm = colmap[cc];
-        K[row][cc] = cm < NV ? C[row * NV + cm] : D[row * NV + (cm - NV)];
-    }
-    for (int row = lane; row < NV; row += 32) K[row][NV] = g[row];
-    __syncwarp();
-    for (int k = 0; k < NV; ++k) {
-        // pivot search (lane-strided rows), then swap rows k <-> p
-        double best = -1.0;
-        int bi = k;
-        for (int row = k + lane; row < NV; row += 32) {
-            const double v = fabs(K[row][k]);
-            if (v > best) { best = v; bi = row; }
-        }
+    const bool row_ok = lane < NV;
+    const int row = row_ok ? lane : 0;
+    double a[NV], b = row_ok ? g[row] : 0.0;
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const double ob = __shfl_xor_sync(RST_FULL_MASK, best, off);
-            const int oi = __shfl_xor_sync(RST_FULL_MASK, bi, off);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
-        if (!(best > 0.0)) { if (lane == 0) atomicOr(flags, RST_FLAG_ZERO_PIVOT); }
-        if (bi != k)
-            for (int c = lane; c <= NV; c += 32) { const double tmp = K[k][c]; K[k][c] = K[bi][c]; K[bi][c] = tmp; }
-        __syncwarp();
-        const double pivval = K[k][k];
-        for (int row = k + 1 + lane; row < NV; row += 32) {
-            const double l = K[row][k] / pivval;
-            for (int c = k + 1; c <= NV; ++c) K[row][c] = fma(-l, K[k][c], K[row][c]);
-        }
-        __syncwarp();
+    for (int cc = 0; cc < NV; ++cc) {
+        const int cm = colmap[cc];
+        a[cc] = row_ok ? (cm < NV ? C[row * NV + cm] : D[row * NV + (cm - NV)]) : 0.0;
+    }
+    bool cand = row_ok;
+    int ps[NV];
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        // exact arg-max over the candidate rows: high word, then low word among the rows that tie on it
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a[k]));
+        const unsigned hi = cand ? (unsigned)(bits >> 32) + 1u : 0u;
+        const unsigned mhi = __reduce_max_sync(RST_FULL_MASK, hi);
+        const bool top = cand && hi == mhi;
+        const unsigned mlo = __reduce_max_sync(RST_FULL_MASK, top ? (unsigned)bits : 0u);
+        const unsigned win = __ballot_sync(RST_FULL_MASK, top && (unsigned)bits == mlo);
+        const int p = win ? (__ffs(win) - 1) : 0;
+        ps[k] = p;
+        const double piv = __shfl_sync(RST_FULL_MASK, a[k], p);
+        bad = bad || !(fabs(piv) > 0.0);
+        const bool upd = cand && lane != p;
+        const double l = upd ? a[k] / piv : 0.0;
+#pragma unroll
+        for (int c = k + 1; c < NV; ++c) a[c] = fma(-l, __shfl_sync(RST_FULL_MASK, a[c], p), a[c]);
+        b = fma(-l, __shfl_sync(RST_FULL_MASK, b, p), b);
+        if (lane == p) cand = false;
+    }
+    if (bad && lane == 0) atomicOr(flags, RST_FLAG_ZERO_PIVOT);
+    // back-substitution in pivot order: row ps[k] determines unknown k
+    double x[NV];
+    bool done = !row_ok;
+#pragma unroll
+    for (int k = NV - 1; k >= 0; --k) {
+        const double xk = __shfl_sync(RST_FULL_MASK, b / a[k], ps[k]);
+        x[k] = xk;
+        if (lane == ps[k]) done = true;
+        if (!done) b = fma(-a[k], xk, b);
     }
     if (lane == 0) {
-        for (int row = NV - 1; row >= 0; --row) {
-            double s = K[row][NV];
-            for (int c = row + 1; c < NV; ++c) s = fma(-K[row][c], K[c][NV], s);
-            K[row][NV] = s / K[row][row];
-        }
         for (int c = 0; c < 2 * NV; ++c) Z[c] = 0.0;
-        for (int cc = 0; cc < NV; ++cc) Z[colmap[cc]] = K[cc][NV];
+#pragma unroll
+        for (int cc = 0; cc < NV; ++cc) Z[colmap[cc]] = x[cc];
     }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(32) abd_top_solve_kernel(const double *C, const double *D, const double *g,
+                                                           double *Z /* [2][nv] */, unsigned long long left_mask,
+                                                           unsigned long long right_mask, unsigned *flags) {
+    __shared__ AbdTopSmem<NV> sm;
+    abd_top_solve_warp<NV>(sm, C, D, g, Z, left_mask, right_mask, flags, threadIdx.x);
 }
 
 }  // namespace rst

@@ -391,11 +391,9 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
 // pivot records (warp-uniform), per block 4 coalesced Lt loads, 4 independent broadcasts of the raw pivot entries, 4 FMA.
 // ------------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(128) abd_forward4_kernel(AbdLevel L) {
+__device__ __forceinline__ void abd_forward4_slab(const AbdLevel &L, int64_t slab, int lane) {
     using Cf = Abd4Cfg<NV>;
     constexpr int R2 = Cf::R2, NB = Cf::NB;
-    const int lane = threadIdx.x & 31;
-    const int64_t slab = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (slab >= L.nslabs) return;
     const int64_t g0 = slab * (int64_t)L.S;
     const int len = (int)((L.n - g0) < (int64_t)L.S ? (L.n - g0) : (int64_t)L.S);
@@ -452,6 +450,74 @@ __global__ void __launch_bounds__(128) abd_forward4_kernel(AbdLevel L) {
         carrymask = cm[NB];
     }
     if ((carrymask >> lane) & 1u) L.r_next[slab * NV + __popc(carrymask & below)] = w;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(128) abd_forward4_kernel(AbdLevel L) {
+    abd_forward4_slab<NV>(L, (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), threadIdx.x & 31);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tail of the level hierarchy: every level with at most ABD_TAIL_ROWS block rows runs inside ONE single-CTA launch per
+// sweep direction (levels separated by block barriers; data moves through HBM / L2 as between launches).  At 10^6 rows
+// the small levels are pure latency: six launches of 10-18 us each per sweep, 20 % of a linear solve
+// (profiles/r02_summary.md).  The backward launch starts with the closure of the last block row (boundary conditions)
+// when the handle owns the whole mesh.
+// ------------------------------------------------------------------------------------------------
+constexpr int ABD_TAIL_ROWS = 256;
+constexpr int ABD_TAIL_MAX_LEVELS = 6;
+constexpr int ABD_TAIL_THREADS = 512;
+
+struct AbdTail {
+    int nlev;
+    int do_top;
+    AbdLevel lv[ABD_TAIL_MAX_LEVELS];   // fine -> coarse
+    const double *C, *D, *g;            // last block row (closure)
+    double *Ztop;
+    unsigned long long left_mask, right_mask;
+};
+
+// every thread of the CTA: pull [p, p + bytes) into L2 (the factors of the small levels were written a whole
+// factorisation ago: without this every elimination step of the tail waits for a DRAM round trip)
+__device__ __forceinline__ void prefetch_l2_range(const void *p, size_t bytes) {
+    const char *c = reinterpret_cast<const char *>(p);
+    for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)blockDim.x * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+}
+
+template <int NV>
+__global__ void __launch_bounds__(ABD_TAIL_THREADS) abd_tail_forward_kernel(AbdTail T) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int l = 0; l < T.nlev; ++l) {
+        prefetch_l2_range(T.lv[l].Lm, (size_t)T.lv[l].n * Abd4Cfg<NV>::LT * sizeof(double));
+        prefetch_l2_range(T.lv[l].piv, (size_t)T.lv[l].n * Abd4Cfg<NV>::PIV_STRIDE);
+    }
+    for (int l = 0; l < T.nlev; ++l) {
+        const AbdLevel &L = T.lv[l];
+        for (int64_t slab = warp; slab < L.nslabs; slab += nwarps) abd_forward4_slab<NV>(L, slab, lane);
+        __syncthreads();   // r_next of this level is the right-hand side of the next one
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(ABD_TAIL_THREADS) abd_tail_backward_kernel(AbdTail T, unsigned *flags) {
+    __shared__ AbdTopSmem<NV> top_sm;
+    constexpr int GPW = 32 / next_pow2(NV);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int l = T.nlev - 1; l >= 0; --l) {
+        prefetch_l2_range(T.lv[l].UEF, (size_t)T.lv[l].n * AbdPack<NV>::UEF * sizeof(double));
+        prefetch_l2_range(T.lv[l].e, (size_t)T.lv[l].n * NV * sizeof(double));
+    }
+    if (T.do_top) {
+        if (warp == 0) abd_top_solve_warp<NV>(top_sm, T.C, T.D, T.g, T.Ztop, T.left_mask, T.right_mask, flags, lane);
+        __syncthreads();
+    }
+    for (int l = T.nlev - 1; l >= 0; --l) {
+        const AbdLevel &L = T.lv[l];
+        const int64_t nw = (L.nslabs + GPW - 1) / GPW;
+        for (int64_t w = warp; w < nw; w += nwarps) abd_backward_warp<NV>(L, w, lane);
+        __syncthreads();   // Z of this level holds the slab end values of the next finer one
+    }
 }
 
 }  // namespace rst

@@ -131,6 +131,9 @@ struct SolverVT {
     void (*reduce)(const ReduceArgs &, int blocks, cudaStream_t);
     void (*top_general)(const double *C, const double *D, const double *g, const double *Ba, const double *ba, int na,
                         const double *Bb, const double *bb, int nb, double *Z, unsigned *flags, cudaStream_t);
+    // single-CTA tail of the level hierarchy (abd4.cuh); nullptr where the block size has no generation-4 kernels
+    void (*tail_forward)(const AbdTail &, cudaStream_t);
+    void (*tail_backward)(const AbdTail &, unsigned *flags, cudaStream_t);
 };
 
 // kernel generation: "v1" = one panel row per lane + shuffle broadcast (abd.cuh); default "v3" (abd3.cuh).  Both write
@@ -213,7 +216,17 @@ struct SolverImpl {
                             const double *Bb, const double *bb, int nb, double *Z, unsigned *flags, cudaStream_t st) {
         abd_top_general_kernel<NV><<<1, 32, 0, st>>>(C, D, g, Ba, ba, na, Bb, bb, nb, Z, flags);
     }
-    static SolverVT vt() { return SolverVT{NV, &factor, &forward, &backward, &top, &residual, &reduce, &top_general}; }
+    static void tail_forward(const AbdTail &T, cudaStream_t st) {
+        if constexpr (HAS_V4) abd_tail_forward_kernel<NV><<<1, ABD_TAIL_THREADS, 0, st>>>(T);
+    }
+    static void tail_backward(const AbdTail &T, unsigned *flags, cudaStream_t st) {
+        if constexpr (HAS_V4) abd_tail_backward_kernel<NV><<<1, ABD_TAIL_THREADS, 0, st>>>(T, flags);
+    }
+    static SolverVT vt() {
+        const bool tail = use_v4() && std::getenv("RST_B200_NO_TAIL") == nullptr;
+        return SolverVT{NV, &factor, &forward, &backward, &top, &residual, &reduce, &top_general,
+                        tail ? &tail_forward : nullptr, tail ? &tail_backward : nullptr};
+    }
 };
 
 // "dynamic shared memory limit raised" flags of the wide-block kernels.  They MUST have internal linkage: function-local
@@ -294,7 +307,7 @@ struct BigImpl {
     static void reduce(const ReduceArgs &a, int blocks, cudaStream_t st) {
         newton_reduce_generic_kernel<<<blocks, 256, 0, st>>>(a);
     }
-    static SolverVT vt(int nv) { return SolverVT{nv, &factor, &forward, &backward, &top, nullptr, &reduce, nullptr}; }   // residual: generic kernel
+    static SolverVT vt(int nv) { return SolverVT{nv, &factor, &forward, &backward, &top, nullptr, &reduce, nullptr, nullptr, nullptr}; }   // residual: generic kernel
 };
 
 static bool use_big_path(int nv) {
@@ -351,6 +364,7 @@ struct rst_b200_solver {
     int ls_policy = RST_B200_LS_AUTO, ls_fallback = RST_B200_FALLBACK_TO_FAER_SPARSE, ls_refine_steps = 0;   // LinearSolverConfig
     std::vector<void *> owned;
     std::vector<LevelBuf> levels;      // local condensation levels (lanes-per-slab kernels)
+    int tail_begin = -1;               // >= 0: levels[tail_begin..] run inside the single-CTA tail launches (abd4.cuh)
     bool use_tps = false;              // nv == 2: thread-per-slab kernels + single-CTA tail (tps.cuh)
     std::vector<TpsLevel> tps_big;     // levels launched one kernel each
     TpsTail tps_tail{};                // all remaining levels
@@ -452,7 +466,9 @@ static int default_slab(int64_t n, int requested) {
     // measured at nv = 12, 1e6 rows (solve ms): S = 8 1.090, 12 1.065, 16 1.049, 32 1.078, 64 1.107 -- longer slabs mean fewer
     // levels but a longer dependent chain per warp; nv = 64: 16 beats 32 as well
     if (n >= (1 << 12)) return 16;
-    return 8;
+    // small levels are latency bound (one dependent chain of S - 1 eliminations per slab): short slabs, more levels --
+    // the levels below ABD_TAIL_ROWS rows share one launch per sweep (abd4.cuh), so extra levels are nearly free
+    return 4;
 }
 
 template <class H>
@@ -708,6 +724,11 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
                 ln = nn;
                 ++depth;
             }
+        }
+        if (!s->use_tps && s->sv.tail_forward && !s->levels.empty()) {
+            int tb = (int)s->levels.size();
+            while (tb > 0 && s->levels[tb - 1].k.n <= ABD_TAIL_ROWS && (int)s->levels.size() - (tb - 1) <= ABD_TAIL_MAX_LEVELS) --tb;
+            if (tb < (int)s->levels.size()) s->tail_begin = tb;
         }
         if (world > 1) {
             LevelBuf lv{};
@@ -1153,6 +1174,21 @@ extern "C" int rst_b200_factor_reduced(rst_b200_solver *s) {
     return RST_B200_OK;
 }
 
+// the levels of the single-CTA tail launches (built per call: set_solution_buffer may have redirected level 0's Z)
+static AbdTail make_tail(const rst_b200_solver *s, bool with_top) {
+    AbdTail T{};
+    T.nlev = (int)s->levels.size() - s->tail_begin;
+    for (int i = 0; i < T.nlev; ++i) T.lv[i] = s->levels[s->tail_begin + i].k;
+    T.do_top = with_top ? 1 : 0;
+    T.C = s->iface_rows;
+    T.D = s->iface_rows + s->nv * s->nv;
+    T.g = s->iface_rhs;
+    T.Ztop = s->Ztop;
+    T.left_mask = s->left_mask;
+    T.right_mask = s->right_mask;
+    return T;
+}
+
 // all-gather of `count` doubles per rank: NVLink peer-memory kernel when the peers are mapped, host callback otherwise
 static int exchange(rst_b200_solver *s, const double *send, double *recv, int64_t count) {
     if (s->p2p_enabled) {
@@ -1303,8 +1339,13 @@ extern "C" int rst_b200_solve_local_forward(rst_b200_solver *s) {
         CUDA_TRY(cudaGetLastError());
         return RST_B200_OK;
     }
-    for (auto &lv : s->levels) {
-        s->sv.forward(lv.k, s->stream);
+    const int n_plain = s->tail_begin >= 0 ? s->tail_begin : (int)s->levels.size();
+    for (int i = 0; i < n_plain; ++i) {
+        s->sv.forward(s->levels[i].k, s->stream);
+        s->launches++;
+    }
+    if (s->tail_begin >= 0) {
+        s->sv.tail_forward(make_tail(s, false), s->stream);
         s->launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -1352,8 +1393,11 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
     } else {
         C = s->iface_rows; D = s->iface_rows + s->nv * s->nv; g = s->iface_rhs;
     }
-    s->sv.top(C, D, g, s->Ztop, s->left_mask, s->right_mask, s->d_flags, s->nv, s->stream);
-    s->launches++;
+    const bool top_in_tail = s->tail_begin >= 0 && !s->have_red && !s->use_tps;   // closure + small levels: one launch
+    if (!top_in_tail) {
+        s->sv.top(C, D, g, s->Ztop, s->left_mask, s->right_mask, s->d_flags, s->nv, s->stream);
+        s->launches++;
+    }
     if (s->have_red) {
         s->sv.backward(s->red.k, s->stream);
         s->launches++;
@@ -1385,7 +1429,11 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
         CUDA_TRY(cudaGetLastError());
         return RST_B200_OK;
     }
-    for (int i = (int)s->levels.size() - 1; i >= 0; --i) {
+    if (s->tail_begin >= 0) {
+        s->sv.tail_backward(make_tail(s, top_in_tail), s->d_flags, s->stream);
+        s->launches++;
+    }
+    for (int i = (s->tail_begin >= 0 ? s->tail_begin : (int)s->levels.size()) - 1; i >= 0; --i) {
         s->sv.backward(s->levels[i].k, s->stream);
         s->launches++;
     }

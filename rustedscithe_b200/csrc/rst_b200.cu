@@ -27,6 +27,7 @@
 #include "btd.cuh"
 #include "p2p.cuh"
 #include "big.cuh"
+#include "bigd.cuh"
 #include "grid.cuh"
 #include "assemble.cuh"
 #include "newton.cuh"
@@ -251,6 +252,19 @@ struct BigImpl {
     static void factor(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
         // default: register-tiled panel (FP64-pipe bound); RST_B200_BIG_V1 selects the first shared-memory-panel kernel
         const bool v1 = std::getenv("RST_B200_BIG_V1") != nullptr;   // read per call: tests toggle it
+        // nv = 64: blocked elimination with the rank-4 updates on the FP64 tensor cores (bigd.cuh); RST_B200_BIG_DFMA keeps
+        // the register-tiled DFMA kernel (same factor layout) for the A/B comparison the north star asks for
+        if (!v1 && L.nv == BigdCfg::NV && std::getenv("RST_B200_BIG_DFMA") == nullptr && std::getenv("RST_B200_BIG_W32") == nullptr) {
+            constexpr int smem = (int)sizeof(BigdSmem);
+            if (ident_b) {
+                cudaFuncSetAttribute(bigd_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                bigd_factor_kernel<true><<<(unsigned)L.nslabs, BigdCfg::THREADS + 128, smem, st>>>(L, flags);
+            } else {
+                cudaFuncSetAttribute(bigd_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                bigd_factor_kernel<false><<<(unsigned)L.nslabs, BigdCfg::THREADS + 128, smem, st>>>(L, flags);
+            }
+            return;
+        }
         if (!v1) {
             // RST_B200_BIG_W32: 32 warps x (4 x 6) tile at 64 registers instead of 16 warps x (8 x 6) at 128 -- measured
             // SLOWER (185 vs 112 ms per 2.5e5 rows: spills + uncoalesced pivot-row stores), kept for experiments

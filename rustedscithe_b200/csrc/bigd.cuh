@@ -167,12 +167,8 @@ __global__ void __launch_bounds__(BigdCfg::THREADS + 128, 1) bigd_factor_kernel(
     bar_named(2, UPD);
 
     // pivot columns of block b (column tile b / 2, half b & 1) -> shared memory, one plane per column
-    auto post_panel = [&](int b) {
-        const int TCB = b >> 1;
-        double2 v = X[0];
-#pragma unroll
-        for (int tc = 1; tc < MT; ++tc) v = (tc == TCB) ? X[tc] : v;   // TCB < 8: only M tiles hold pivot columns
-        if (hi == ((b & 1) != 0)) {
+    auto post_panel = [&](const double2 &v, bool blk_hi) {
+        if (hi == blk_hi) {
             sm.pan[q & 1][row] = v.x;          // column 2 (q & 1)     -> plane (q & 1)
             sm.pan[2 + (q & 1)][row] = v.y;    // column 2 (q & 1) + 1 -> plane 2 + (q & 1)
         }
@@ -205,12 +201,12 @@ __global__ void __launch_bounds__(BigdCfg::THREADS + 128, 1) bigd_factor_kernel(
         }
         bar_named(2, UPD);   // tmap / pv of the previous block row are consumed
         if (tid < R2) sm.pv[tid] = -1;
-        post_panel(0);
+        post_panel(X[0], false);
         bar_named(1, ALL);   // A(0)
         bar_named(1, ALL);   // B(0)
 
-#pragma unroll 1
-        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {            // fully unrolled: every tile index below is a compile-time constant
             const int TCB = b >> 1;
             const int TN = (b + 1) >> 1;           // column tile that holds the pivot columns of block b + 1
             const bool more = b + 1 < NB;
@@ -229,10 +225,8 @@ __global__ void __launch_bounds__(BigdCfg::THREADS + 128, 1) bigd_factor_kernel(
             const double *bsrc = &sm.xs[q][gid];
             // ---- look-ahead: update the tile with the next block's pivot columns first and hand them to the panel warps ----
             if (more) {
-#pragma unroll
-                for (int tc = 0; tc < MT; ++tc)
-                    if (tc == TN) dmma_m8n8k4(X[tc], af, bsrc[8 * tc]);
-                post_panel(b + 1);
+                dmma_m8n8k4(X[TN], af, bsrc[8 * TN]);
+                post_panel(X[TN], ((b + 1) & 1) != 0);
                 bar_named(1, ALL);   // A(b + 1): the panel warps factor block b + 1 while the rest of block b is applied
             }
             // ---- X <- X - Lt X[pivot rows] on the remaining tiles ------------------------------------------------------------

@@ -400,15 +400,24 @@ __device__ __forceinline__ void abd_forward4_slab(const AbdLevel &L, int64_t sla
     const unsigned below = lanes_below(lane);
     unsigned carrymask = (1u << NV) - 1u;
     double w = lane < NV ? L.r[g0 * NV + lane] : 0.0;
+    // pivot records run one block row ahead of the chain: the multiplier addresses depend on them, so fetching them inside
+    // the step would put two dependent memory round trips on every step of the (latency-bound) small levels
+    unsigned pnext[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) pnext[b] = len > 1 ? __ldg(reinterpret_cast<const unsigned *>(L.piv + (g0 + 1) * (int64_t)Cf::PIV_STRIDE) + b) : 0u;
     for (int i = 1; i < len; ++i) {
         const int64_t g = g0 + i;
         const double *lt_g = L.Lm + g * (int64_t)Cf::LT;
         if (L.prefetch && i + 1 < len && lane * 128 < Cf::LT * 8)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(lt_g + Cf::LT) + lane * 128));
-        const unsigned *pw = reinterpret_cast<const unsigned *>(L.piv + g * (int64_t)Cf::PIV_STRIDE);
         unsigned pword[NB];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) pword[b] = __ldg(pw + b);
+        for (int b = 0; b < NB; ++b) pword[b] = pnext[b];
+        if (i + 1 < len) {
+            const unsigned *pw = reinterpret_cast<const unsigned *>(L.piv + (g + 1) * (int64_t)Cf::PIV_STRIDE);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) pnext[b] = __ldg(pw + b);
+        }
         const unsigned freemask = ~carrymask & Cf::ALL;
         if ((freemask >> lane) & 1u) w = L.r[g * NV + __popc(freemask & below)];
         // all multiplier loads of the block row up front (independent of the chain)
@@ -464,7 +473,7 @@ __global__ void __launch_bounds__(128) abd_forward4_kernel(AbdLevel L) {
 // (profiles/r02_summary.md).  The backward launch starts with the closure of the last block row (boundary conditions)
 // when the handle owns the whole mesh.
 // ------------------------------------------------------------------------------------------------
-constexpr int ABD_TAIL_ROWS = 256;
+constexpr int ABD_TAIL_ROWS = 64;    // one slab per warp at the largest tail level: a single CTA cannot hide DRAM latency with several slabs per warp
 constexpr int ABD_TAIL_MAX_LEVELS = 6;
 constexpr int ABD_TAIL_THREADS = 512;
 

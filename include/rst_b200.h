@@ -214,6 +214,17 @@ int64_t rst_b200_jacobian_structure(rst_b200_solver *s, int64_t *rows, int64_t *
 /* ---- the reference's AOT artefact ABI (codegen_c_aot_library.rs:376-409), bound to one handle ---- */
 /* args = [params..., y_reduced...]; returns 1 ok / 0 on NULL pointer or length mismatch (:382-384) */
 int rst_b200_aot_bind(rst_b200_solver *s);
+/* Re-entrancy (the reference calls the artefact's symbols from rayon worker threads, symbolic_functions_BVP.rs:2308-2357,
+ * and marks the linked library Send + Sync, codegen_aot_runtime_link.rs:21-36): rst_b200_aot_bind binds the calling thread
+ * AND the library-wide default that threads without a binding of their own use; rst_b200_aot_bind_thread binds the calling
+ * thread only.  Concurrent calls on one handle are serialised by the handle, calls on different handles run concurrently.
+ * Every AOT artefact (.so) carries its own binding. */
+int rst_b200_aot_bind_thread(rst_b200_solver *s);
+/* manifest.h of the reference's C AOT artefacts (codegen_c_aot_library.rs:250-278) for this handle, in the reference's
+ * exact text format: BACKEND_KIND "aot", MATRIX_BACKEND "banded", RESIDUAL_LEN, JACOBIAN_ROWS / _COLS, JACOBIAN_NNZ,
+ * RESIDUAL_FN_NAME "eval_residual", JACOBIAN_FN_NAME "eval_banded_values" (codegen_runtime_api.rs:1100).  Returns the
+ * length without the terminating NUL, -1 if cap is too small. */
+int64_t rst_b200_manifest_h(rst_b200_solver *s, char *buf, size_t cap);
 int rustedscithe_aot_eval_residual(const double *args, size_t args_len, double *out, size_t out_len);
 int rustedscithe_aot_eval_jacobian_values(const double *args, size_t args_len, double *out, size_t out_len);
 

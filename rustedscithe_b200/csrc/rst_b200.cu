@@ -17,6 +17,7 @@
 #include <atomic>
 #include <chrono>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -230,22 +231,14 @@ struct SolverImpl {
     }
 };
 
-// "dynamic shared memory limit raised" flags of the wide-block kernels.  They MUST have internal linkage: function-local
-// statics of inline / template functions are STB_GNU_UNIQUE symbols, i.e. ONE object per process even across dlopen'ed
-// libraries -- a second library (AOT artefact) would then skip cudaFuncSetAttribute for ITS copy of the kernel and fail to launch.
-static bool g_big_attr_done[8] = {false, false, false, false, false, false, false, false};
-
 // wide blocks (16 < nv <= 64, or any nv >= 3 with RST_B200_FORCE_BIG): run-time-nv block-per-slab kernels (big.cuh)
 struct BigImpl {
     template <int NVP, int NW>
     static void factor_tiled(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
         using C = BigrCfg<NVP, NW>;
-        bool &attr_set = g_big_attr_done[(NVP > 32 ? 1 : 0) + (NW > 16 ? 2 : 0)];
-        if (!attr_set) {
-            cudaFuncSetAttribute(bigr_factor_kernel<NVP, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
-            cudaFuncSetAttribute(bigr_factor_kernel<NVP, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
-            attr_set = true;
-        }
+        // the opt-in is per device and per loaded module: set it on every launch (cheap), never cache it per process
+        cudaFuncSetAttribute(bigr_factor_kernel<NVP, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
+        cudaFuncSetAttribute(bigr_factor_kernel<NVP, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes);
         if (ident_b) bigr_factor_kernel<NVP, NW, true><<<(unsigned)L.nslabs, C::THREADS, C::smem_bytes, st>>>(L, L.nv, flags);
         else bigr_factor_kernel<NVP, NW, false><<<(unsigned)L.nslabs, C::THREADS, C::smem_bytes, st>>>(L, L.nv, flags);
     }
@@ -275,12 +268,8 @@ struct BigImpl {
             return;
         }
         const size_t smem = big_factor_smem_bytes(L.nv);
-        bool &attr_set = g_big_attr_done[4];
-        if (!attr_set) {
-            cudaFuncSetAttribute(big_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_factor_smem_bytes(BIG_MAX_NV));
-            cudaFuncSetAttribute(big_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_factor_smem_bytes(BIG_MAX_NV));
-            attr_set = true;
-        }
+        cudaFuncSetAttribute(big_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_factor_smem_bytes(BIG_MAX_NV));
+        cudaFuncSetAttribute(big_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_factor_smem_bytes(BIG_MAX_NV));
         if (ident_b) big_factor_kernel<true><<<(unsigned)L.nslabs, BIG_THREADS, smem, st>>>(L, L.nv, flags);
         else big_factor_kernel<false><<<(unsigned)L.nslabs, BIG_THREADS, smem, st>>>(L, L.nv, flags);
     }
@@ -295,11 +284,7 @@ struct BigImpl {
             big_forward_kernel<<<(unsigned)L.nslabs, 128, 0, st>>>(L, L.nv);
             return;
         }
-        bool &attr_set = g_big_attr_done[5];
-        if (!attr_set) {
-            cudaFuncSetAttribute(bigp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bigp_forward_smem(BIG_MAX_NV));
-            attr_set = true;
-        }
+        cudaFuncSetAttribute(bigp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bigp_forward_smem(BIG_MAX_NV));
         bigp_forward_kernel<<<(unsigned)L.nslabs, BIGP_THREADS, bigp_forward_smem(L.nv), st>>>(L, L.nv);
     }
     static void backward(const AbdLevel &L, cudaStream_t st) {
@@ -307,11 +292,7 @@ struct BigImpl {
             big_backward_kernel<<<(unsigned)L.nslabs, 64, 0, st>>>(L, L.nv);
             return;
         }
-        bool &attr_set = g_big_attr_done[6];
-        if (!attr_set) {
-            cudaFuncSetAttribute(bigp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bigp_backward_smem(BIG_MAX_NV));
-            attr_set = true;
-        }
+        cudaFuncSetAttribute(bigp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bigp_backward_smem(BIG_MAX_NV));
         bigp_backward_kernel<<<(unsigned)L.nslabs, BIGP_THREADS, bigp_backward_smem(L.nv), st>>>(L, L.nv);
     }
     static void top(const double *C, const double *D, const double *g, double *Z, unsigned long long lm,
@@ -375,6 +356,7 @@ struct rst_b200_solver {
     double *d_tmp = nullptr;  // [n*nv + nv] staging for reduced-order host drop-ins
     double *ref_b = nullptr, *ref_x = nullptr, *ref_xt = nullptr;   // guarded refinement: rhs copy, iterate, trial iterate
     unsigned long long *ref_norm = nullptr;
+    std::mutex aot_mtx;   // serialises the handle-less AOT symbols on this handle (the reference may call them from several rayon threads)
     int ls_policy = RST_B200_LS_AUTO, ls_fallback = RST_B200_FALLBACK_TO_FAER_SPARSE, ls_refine_steps = 0;   // LinearSolverConfig
     std::vector<void *> owned;
     std::vector<LevelBuf> levels;      // local condensation levels (lanes-per-slab kernels)
@@ -454,7 +436,14 @@ static P2pIface iface_args(const rst_b200_solver *s, bool fused) {
     return I;
 }
 
-static rst_b200_solver *g_bound = nullptr;  // handle behind the reference's handle-less AOT symbols
+// Handle behind the reference's handle-less AOT symbols.  rst_b200_aot_bind binds for the CALLING THREAD and, the first
+// time (or when the previous default goes away), process-wide: a thread that never bound anything -- a rayon worker the
+// reference dispatches chunk calls to (symbolic_functions_BVP.rs:2308-2357) -- uses the library-wide default, threads that
+// bound their own handle are isolated from each other.  Calls on one handle are serialised by its mutex.  Every AOT
+// artefact (.so) has its own copy of these variables, i.e. its own binding.
+static std::atomic<rst_b200_solver *> g_bound{nullptr};
+static thread_local rst_b200_solver *t_bound = nullptr;
+static rst_b200_solver *aot_current() { return t_bound ? t_bound : g_bound.load(std::memory_order_acquire); }
 
 template <class H, class T>
 static int dev_alloc(H *s, T **p, size_t count) {
@@ -781,7 +770,11 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
 
 extern "C" void rst_b200_destroy(rst_b200_solver *s) {
     if (!s) return;
-    if (g_bound == s) g_bound = nullptr;
+    {
+        rst_b200_solver *expect = s;
+        g_bound.compare_exchange_strong(expect, nullptr);
+        if (t_bound == s) t_bound = nullptr;
+    }
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto *cache : {&s->step_graphs, &s->jac_graphs, &s->frozen_graphs})
@@ -2075,14 +2068,39 @@ extern "C" int64_t rst_b200_jacobian_structure(rst_b200_solver *s, int64_t *rows
 }
 
 extern "C" int rst_b200_aot_bind(rst_b200_solver *s) {
-    g_bound = s;
+    t_bound = s;
+    g_bound.store(s, std::memory_order_release);
     return RST_B200_OK;
+}
+// bind for the calling thread only (the process-wide default is left alone)
+extern "C" int rst_b200_aot_bind_thread(rst_b200_solver *s) {
+    t_bound = s;
+    return RST_B200_OK;
+}
+
+// manifest.h of the reference's AOT artefacts (codegen_c_aot_library.rs:250-278) for this handle, byte for byte in the
+// reference's format; returns the length (excluding the terminating NUL) or -1 when `cap` is too small.
+extern "C" int64_t rst_b200_manifest_h(rst_b200_solver *s, char *buf, size_t cap) {
+    if (!s || s->world != 1) return -1;
+    build_structure(s);
+    const long long n = (long long)(s->N * (int64_t)s->nv);
+    char tmp[1024];
+    const int len = std::snprintf(tmp, sizeof(tmp),
+        "/* AUTO-GENERATED C AOT MANIFEST */\n\n#ifndef MANIFEST_H\n#define MANIFEST_H\n\n#define BACKEND_KIND \"aot\"\n"
+        "#define MATRIX_BACKEND \"banded\"\n#define RESIDUAL_LEN %lld\n#define JACOBIAN_ROWS %lld\n#define JACOBIAN_COLS %lld\n"
+        "#define JACOBIAN_NNZ %lld\n#define RESIDUAL_FN_NAME \"eval_residual\"\n#define JACOBIAN_FN_NAME \"eval_banded_values\"\n\n"
+        "#endif /* MANIFEST_H */\n", n, n, n, (long long)s->st_rows.size());
+    if (len < 0 || (size_t)len + 1 > cap || !buf) return -1;
+    std::memcpy(buf, tmp, (size_t)len + 1);
+    return len;
 }
 
 // codegen_c_aot_library.rs:376-389: returns 1 ok / 0 on null pointers or out_len mismatch
 extern "C" int rustedscithe_aot_eval_residual(const double *args, size_t args_len, double *out, size_t out_len) {
-    rst_b200_solver *s = g_bound;
+    rst_b200_solver *s = aot_current();
     if (!s || !args || !out || s->world != 1) return 0;
+    std::lock_guard<std::mutex> lock(s->aot_mtx);
+    if (cudaSetDevice(s->device) != cudaSuccess) return 0;   // the caller may be a fresh worker thread
     const size_t n = (size_t)(s->N * (int64_t)s->nv);
     if (out_len != n || args_len != n + (size_t)s->np) return 0;
     if (s->np > 0 && cudaMemcpyAsync(s->d_params, args, s->np * sizeof(double), cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return 0;
@@ -2095,8 +2113,10 @@ extern "C" int rustedscithe_aot_eval_residual(const double *args, size_t args_le
 
 // codegen_c_aot_library.rs:391-409: nnz values in the manifest's entry order
 extern "C" int rustedscithe_aot_eval_jacobian_values(const double *args, size_t args_len, double *out, size_t out_len) {
-    rst_b200_solver *s = g_bound;
+    rst_b200_solver *s = aot_current();
     if (!s || !args || !out || s->world != 1) return 0;
+    std::lock_guard<std::mutex> lock(s->aot_mtx);
+    if (cudaSetDevice(s->device) != cudaSuccess) return 0;
     const size_t n = (size_t)(s->N * (int64_t)s->nv);
     build_structure(s);
     const size_t nnz = s->st_rows.size();

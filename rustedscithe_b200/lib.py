@@ -102,6 +102,8 @@ SYMBOLS = {
     "rst_b200_solve_multiple_in_place": (C.c_int, [_H, c_f64_p, C.c_size_t, C.c_size_t]),
     "rst_b200_jacobian_structure": (C.c_int64, [_H, c_i64_p, c_i64_p, c_i64_p, c_i64_p, c_int_p, c_int_p]),
     "rst_b200_aot_bind": (C.c_int, [_H]),
+    "rst_b200_aot_bind_thread": (C.c_int, [_H]),
+    "rst_b200_manifest_h": (C.c_int64, [_H, C.c_char_p, C.c_size_t]),
     "rustedscithe_aot_eval_residual": (C.c_int, [c_f64_p, C.c_size_t, c_f64_p, C.c_size_t]),
     "rustedscithe_aot_eval_jacobian_values": (C.c_int, [c_f64_p, C.c_size_t, c_f64_p, C.c_size_t]),
     "rst_b200_set_allgather": (C.c_int, [_H, ALLGATHER_FN, C.c_void_p]),

@@ -195,8 +195,11 @@ class NRBVP:
             t["number of solving linear systems"] += self.stats.linear_solves
             t["number of jacobians recalculations"] += self.stats.jac_recalcs
             if self.stats.status != 1:
-                # the reference would refine from the last converged result here (:2145-2154); without one it has
-                # nothing to refine -- a failed solve ends the adaptive loop
+                # Deliberate deviation, documented in DESIGN.md: after a FAILED solve the reference calls
+                # try_solve_with_new_grid (:2145-2154), whose create_new_grid unwraps self.result -- a panic when no grid has
+                # converged yet, and after a refinement a size mismatch between the saved result (previous mesh) and the
+                # already replaced x_mesh (DMatrix::from_column_slice panics, :2216-2217).  There is no defined behaviour
+                # to mirror, so a failed solve ends the adaptive loop with None and keeps the last converged result.
                 self.result = None if self.grid_refinements == 0 else self.result
                 return None
             self.result = self.get_state()

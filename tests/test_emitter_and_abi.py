@@ -157,3 +157,24 @@ def test_emitted_cuda_c_text_evaluates_like_the_oracle_on_the_host(key, tmp_path
     J = J.reshape(nv, nv)
     assert np.max(np.abs(J - J_orc) / (np.abs(J_orc) + 1e-12 * np.max(np.abs(J_orc)) + 1e-300)) < 1e-12
     assert np.array_equal(J != 0.0, np.array(em.pattern).reshape(nv, nv) != 0)
+
+
+def test_manifest_h_matches_the_reference_format_and_the_oracle_structure():
+    """f3: manifest.h as the reference's C AOT library writer emits it (codegen_c_aot_library.rs:250-278), with the entry
+    count of the oracle's BandedJacobianStructure."""
+    from oracle import oracle as orc
+    from rustedscithe_b200 import build as rbuild
+    from rustedscithe_b200 import problems
+    for key, n, scheme in (("linear2", 80, "forward"), ("flame12", 33, "forward"), ("combustion6", 50, "trapezoid"),
+                           ("coupled64", 7, "forward")):
+        spec = problems.get(key)
+        o = orc.OracleBVP(key, n, spec.bc_list(), t0=spec.t0, t_end=spec.t_end, scheme=scheme)
+        rows = o.structure()[0]
+        text = rbuild.manifest_h(spec, n, scheme)
+        nn = spec.nv * n
+        assert text == ("/* AUTO-GENERATED C AOT MANIFEST */\n\n#ifndef MANIFEST_H\n#define MANIFEST_H\n\n"
+                        "#define BACKEND_KIND \"aot\"\n#define MATRIX_BACKEND \"banded\"\n"
+                        f"#define RESIDUAL_LEN {nn}\n#define JACOBIAN_ROWS {nn}\n#define JACOBIAN_COLS {nn}\n"
+                        f"#define JACOBIAN_NNZ {rows.shape[0]}\n"
+                        "#define RESIDUAL_FN_NAME \"eval_residual\"\n#define JACOBIAN_FN_NAME \"eval_banded_values\"\n\n"
+                        "#endif /* MANIFEST_H */\n")

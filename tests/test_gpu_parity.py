@@ -485,3 +485,49 @@ def _read(ptr, count):
     out = np.zeros(count)
     assert rlib.load().rst_b200_memcpy(out.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), count * 8, 2) == 0
     return out
+
+
+def test_manifest_and_reentrant_aot_symbols():
+    """f3 + boundary: the handle writes the reference's manifest.h; the handle-less AOT symbols can be driven from several
+    threads, each bound to its own handle (rst_b200_aot_bind_thread), and give the single-threaded answers."""
+    import ctypes as C
+    import threading
+    from rustedscithe_b200 import build as rbuild
+    cases = [("flame12", 700), ("combustion6", 900), ("linear2", 4000)]
+    handles, ys, want = [], [], []
+    rng = np.random.default_rng(77)
+    for key, n in cases:
+        spec = problems.get(key)
+        g = _gpu(key, n)
+        buf = C.create_string_buffer(2048)
+        ln = g.L.rst_b200_manifest_h(g.handle, buf, 2048)
+        assert ln > 0 and buf.value.decode() == rbuild.manifest_h(spec, n)
+        assert g.L.rst_b200_manifest_h(g.handle, buf, 16) == -1
+        y = 0.35 + 0.6 * rng.random(spec.nv * n)
+        handles.append(g); ys.append(y); want.append((g.fun_call(y), g.jac_call(y)))
+    got = [None] * len(cases)
+
+    def worker(i):
+        g, y = handles[i], ys[i]
+        L = g.L
+        L.rst_b200_aot_bind_thread(g.handle)
+        n = y.shape[0]
+        nnz = want[i][1].shape[0]
+        p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        rs, js = [], []
+        for _ in range(8):
+            r, j = np.zeros(n), np.zeros(nnz)
+            assert L.rustedscithe_aot_eval_residual(p(y), n, p(r), n) == 1
+            assert L.rustedscithe_aot_eval_jacobian_values(p(y), n, p(j), nnz) == 1
+            rs.append(r); js.append(j)
+        got[i] = (rs, js)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(cases))]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    for i in range(len(cases)):
+        assert got[i] is not None
+        for r, j in zip(*got[i]):
+            assert np.array_equal(r, want[i][0]) and np.array_equal(j, want[i][1])
+    for g in handles:
+        g.close()

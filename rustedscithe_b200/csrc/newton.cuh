@@ -178,13 +178,16 @@ __global__ void __launch_bounds__(256) newton_reduce_final_kernel(const double *
     if (world > 1) {
         p2p_allgather_block(peers, out, 8, gscal, rank, world, pay, seq, flags);
         if (threadIdx.x == 0) {
-            double c0 = 0.0, c1 = 0.0, c2 = 1.0, c3 = 0.0, c4 = 0.0;
+            double c0 = 0.0, c1 = 0.0, c2 = 1.0, c3 = 0.0;
+            unsigned c4 = flags[0] | flags[2];
             for (int p = 0; p < world; ++p) {
                 c0 += gscal[8 * p]; c1 += gscal[8 * p + 1]; c2 = fmin(c2, gscal[8 * p + 2]);
-                c3 = fmax(c3, gscal[8 * p + 3]); c4 = fmax(c4, gscal[8 * p + 4]);
+                c3 = fmax(c3, gscal[8 * p + 3]);
+                const double f = gscal[8 * p + 4];
+                c4 |= (f == f && f >= 0.0 && f < 4.0e9) ? (unsigned)f : RST_FLAG_PEER_TIMEOUT;   // a NaN word = poisoned exchange
             }
             out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-            out[4] = fmax(c4, (double)(flags[0] | flags[2]));
+            out[4] = (double)c4;
         }
     }
 }

@@ -1441,9 +1441,13 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
         s->launches++;
     }
     for (int i = (s->tail_begin >= 0 ? s->tail_begin : (int)s->levels.size()) - 1; i >= 0; --i) {
+        // (a level-0 sweep with the damping reductions fused in, as the nv = 2 path has, was measured 80 us SLOWER per solve at
+        // nv = 12 than sweep + newton_reduce_kernel: the extra state loads and registers cost the sweep more HBM efficiency
+        // than the separate 58 us pass costs)
         s->sv.backward(s->levels[i].k, s->stream);
         s->launches++;
     }
+    s->fuse_reduce_state = -1;
     CUDA_TRY(cudaGetLastError());
     return RST_B200_OK;
 }
@@ -1561,7 +1565,8 @@ static void set_solution_buffer(rst_b200_solver *s, double *buf) {
 
 // ---- damped Newton -------------------------------------------------------------------------------
 static int check_scalars(const rst_b200_scalars &sc) {
-    if (sc.nan_flag != 0.0) return fail(RST_B200_ERR_NAN, "NaN in residual or Newton step");
+    if (sc.nan_flag != 0.0 || (((unsigned)sc.device_flags) & RST_FLAG_NAN_F))
+        return fail(RST_B200_ERR_NAN, "NaN in residual or Newton step");
     if (((unsigned)sc.device_flags) & RST_FLAG_PEER_TIMEOUT) return fail(RST_B200_ERR_CUDA, "a peer rank never arrived at the interface exchange");
     if (((unsigned)sc.device_flags) & RST_FLAG_ZERO_PIVOT) return fail(RST_B200_ERR_ZERO_PIVOT, "zero pivot in block elimination");
     return RST_B200_OK;

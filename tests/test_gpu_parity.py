@@ -531,3 +531,21 @@ def test_manifest_and_reentrant_aot_symbols():
             assert np.array_equal(r, want[i][0]) and np.array_equal(j, want[i][1])
     for g in handles:
         g.close()
+
+
+@pytest.mark.parametrize("key,n_steps", [("flame12", 600), ("linear2", 3000), ("combustion6", 500), ("coupled64", 40)])
+def test_nan_in_the_state_is_reported_not_propagated(key, n_steps):
+    """NRBVP::step scans F and the step for NaN and panics (NR_Damp_solver_damped.rs:1821-1826, :1839-1844); the library
+    returns RST_B200_ERR_NAN."""
+    from rustedscithe_b200 import lib as rlib
+    spec = problems.get(key)
+    y0 = spec.guess(n_steps).copy()
+    y0[y0.shape[0] // 2] = np.nan
+    g = _gpu(key, n_steps, guess=y0)
+    with pytest.raises(rlib.RstB200Error) as e:
+        g.try_solve()
+    assert e.value.code == rlib.ERR_NAN
+    # the handle stays usable: a clean state solves normally afterwards
+    g.set_state(spec.guess(n_steps))
+    assert g.try_solve() is not None
+    g.close()

@@ -195,7 +195,10 @@ enum rst_b200_fallback_policy {                 /* FallbackPolicy, solver_policy
 /* Defaults mirror LinearSolverConfig::default(): Auto, ToFaerSparse, 0 refinement steps.  Auto / ForceBanded /
  * ForceBlockTridiagonal* all select the pivoted condensation solver (it handles both matrix classes, including the node
  * blocks the reference's block solver rejects).  iterative_refinement_steps > 0 makes rst_b200_solve_in_place /
- * _solve_multiple_in_place run the guarded refinement below with tol = 1e-12 (linear_solver.rs:84-101). */
+ * _solve_multiple_in_place run the guarded refinement below with tol = 1e-12 (linear_solver.rs:84-101); 0 = never (the
+ * reference's default).  A fresh handle holds -1 = library default: one guarded step (tol 0) on meshes of >= 4096 intervals,
+ * none below -- the condensation has the banded LU's backward error, but its forward error grows with the mesh and passes
+ * 1e-10 there.  The Newton drivers never refine. */
 int rst_b200_set_linear_solver_config(rst_b200_solver *s, int policy, int fallback, int iterative_refinement_steps);
 int rst_b200_get_linear_solver_config(const rst_b200_solver *s, int *policy, int *fallback, int *iterative_refinement_steps);
 /* solve_in_place_with_refinement (lapack_style_banded.rs:1227-1298): solve, then at most max_iters guarded steps of

@@ -357,7 +357,10 @@ struct rst_b200_solver {
     double *ref_b = nullptr, *ref_x = nullptr, *ref_xt = nullptr;   // guarded refinement: rhs copy, iterate, trial iterate
     unsigned long long *ref_norm = nullptr;
     std::mutex aot_mtx;   // serialises the handle-less AOT symbols on this handle (the reference may call them from several rayon threads)
-    int ls_policy = RST_B200_LS_AUTO, ls_fallback = RST_B200_FALLBACK_TO_FAER_SPARSE, ls_refine_steps = 0;   // LinearSolverConfig
+    // LinearSolverConfig.  ls_refine_steps < 0 = library default: the DirectLinearSolver drop-ins take ONE guarded refinement step
+    // (tol 0: only the "residual must decrease" guard ends it) on meshes of >= 4096 intervals, where the forward error of the
+    // condensation exceeds the 1e-10 contract; the Newton loop never refines
+    int ls_policy = RST_B200_LS_AUTO, ls_fallback = RST_B200_FALLBACK_TO_FAER_SPARSE, ls_refine_steps = -1;
     std::vector<void *> owned;
     std::vector<LevelBuf> levels;      // local condensation levels (lanes-per-slab kernels)
     int tail_begin = -1;               // >= 0: levels[tail_begin..] run inside the single-CTA tail launches (abd4.cuh)
@@ -1896,6 +1899,8 @@ extern "C" int rst_b200_solve_in_place(rst_b200_solver *s, double *rhs, size_t l
     if ((int64_t)len != s->N * (int64_t)s->nv) return fail(RST_B200_ERR_INVALID, "rhs length mismatch");
     if (s->ls_refine_steps > 0)   // LinearSolver::solve_in_place with iterative_refinement_steps > 0 (linear_solver.rs:84-101): tol 1e-12
         return rst_b200_solve_in_place_with_refinement(s, rhs, len, s->ls_refine_steps, 1e-12, nullptr, nullptr);
+    if (s->ls_refine_steps < 0 && s->N >= 4096)   // library default at size: one guarded step
+        return rst_b200_solve_in_place_with_refinement(s, rhs, len, 1, 0.0, nullptr, nullptr);
     // rows are interval-major already (row j*nv+i): rhs -> F, solve, gather dY in reduced column order
     CUDA_TRY(cudaMemcpyAsync(s->F, rhs, len * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     TRY(rst_b200_solve(s));
@@ -1917,7 +1922,7 @@ extern "C" int rst_b200_set_linear_solver_config(rst_b200_solver *s, int policy,
     if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
     if (policy < RST_B200_LS_AUTO || policy > RST_B200_LS_FORCE_FAER_SPARSE) return fail(RST_B200_ERR_INVALID, "unknown LinearSolverPolicy");
     if (fallback != RST_B200_FALLBACK_NEVER && fallback != RST_B200_FALLBACK_TO_FAER_SPARSE) return fail(RST_B200_ERR_INVALID, "unknown FallbackPolicy");
-    if (iterative_refinement_steps < 0) return fail(RST_B200_ERR_INVALID, "negative refinement budget");
+    if (iterative_refinement_steps < -1) return fail(RST_B200_ERR_INVALID, "refinement budget must be >= 0 (or -1: library default)");
     if (policy == RST_B200_LS_FORCE_GENERAL_BANDED_PARTIAL_PIVOT || policy == RST_B200_LS_FORCE_FAER_SPARSE)
         return fail(RST_B200_ERR_UNSUPPORTED, "dense general-pivot and faer sparse LU are CPU diagnostic back-ends of the reference; "
                                               "the B200 library has the pivoted condensation solver only (no CPU fallback)");

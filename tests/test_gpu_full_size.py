@@ -11,7 +11,9 @@
         measured in the same test: the change of the banded LU's OWN answer when every Jacobian entry moves by one unit
         in the last place (3e-10 at 10^6 flame points: below that, "agreement with the reference" is not defined, the
         reference would not agree with itself on another libm).  Measured: 3e-14 (C2), 2.1e-10 (C3), 1.8e-11 (64 var.);
-      - forward agreement of the plain solve: recorded and bounded by 1e-7.  tools/forward_error_probe.py (exact
+      - the library default of the drop-in (`rst_b200_solve_in_place` on a fresh handle takes one guarded step on meshes of
+        >= 4096 intervals) against the PLAIN banded LU: same bound;
+      - forward agreement of the plain solve (refinement switched off, as the Newton loop runs): recorded, bounded by 1e-7.  tools/forward_error_probe.py (exact
         solution from extended-precision refinement) shows why 1e-10 cannot hold for it at these sizes: the
         hierarchical condensation has the banded LU's backward error but a forward error that grows with the mesh
         (1.5e-10 / 1.5e-9 / 1.1e-8 at 10^4 / 10^5 / 10^6 flame points; banded LU 2e-11 .. 7e-11) -- the rounding of the
@@ -69,6 +71,7 @@ def test_first_newton_step_matches_the_banded_lu_at_full_size(key, n_steps):
     dy_ref = o.solve_banded(vals, rhs)
     t_cpu = time.time() - t0
     g = NRBVP(key, None, n_steps, DampedSolverOptions.from_spec(spec))
+    g.set_linear_solver_config("Auto", "ToFaerSparse", 0)     # the reference's default: plain solves first
     g.set_state(y)
     g.eval_jacobian()
     g.factor()
@@ -100,6 +103,10 @@ def test_first_newton_step_matches_the_banded_lu_at_full_size(key, n_steps):
     t_cpu += time.time() - t1
     dy_r, acc_gpu, rr_gpu = g.solve_in_place_with_refinement(rhs, 2, 1e-30)
     err_r = float(np.linalg.norm(dy_r - dy_ref_r) / np.linalg.norm(dy_ref_r))
+    # the library default (a fresh handle: one guarded step on meshes of >= 4096 intervals) against the PLAIN banded LU
+    g.set_linear_solver_config("Auto", "ToFaerSparse", -1)
+    dy_def = g.solve_in_place(rhs)
+    err_def = float(np.linalg.norm(dy_def - dy_ref) / np.linalg.norm(dy_ref))
     # sensitivity floor of the reference's own solve: one-ulp relative perturbation of every Jacobian entry
     t1 = time.time()
     sign = np.where(rng.random(vals.shape[0]) < 0.5, -1.0, 1.0)
@@ -114,14 +121,15 @@ def test_first_newton_step_matches_the_banded_lu_at_full_size(key, n_steps):
     res_ref = float(np.linalg.norm(orc.banded_matvec(o.n, kl, ku, banded, dy_ref) - rhs) / np.linalg.norm(rhs))
     print(f"\n{key} N={n_steps}: same matrix |dy - dy_ref|_2/|dy_ref|_2 = {err:.3e}, inf-norm {err_inf:.3e}; "
           f"|J dy - F|/|F|: gpu {res_gpu:.2e}, banded LU {res_ref:.2e}; own Jacobian ({n_diff} of {int(m.sum())} entries differ "
-          f"in the last bits): {err_own:.3e}; refined (gpu {acc_gpu} / oracle {acc_ref} accepted steps): {err_r:.3e}; "
+          f"in the last bits): {err_own:.3e}; refined (gpu {acc_gpu} / oracle {acc_ref} accepted steps): {err_r:.3e}; library default vs plain LU {err_def:.3e}; "
           f"1-ulp sensitivity floor of the banded LU: {floor:.3e}; oracle {t_cpu:.1f} s")
     _record({"test": "first_step", "problem": key, "n_steps": n_steps, "rel_err_2": err, "rel_err_inf": err_inf,
              "residual_gpu": res_gpu, "residual_banded_lu": res_ref, "rel_err_2_own_jacobian": err_own,
              "jacobian_entries_differing": n_diff, "jacobian_entries": int(m.sum()), "oracle_seconds": t_cpu,
-             "rel_err_2_refined": err_r, "one_ulp_sensitivity_floor": floor, "refinement_steps_gpu": acc_gpu, "refinement_steps_oracle": acc_ref})
+             "rel_err_2_refined": err_r, "rel_err_2_library_default": err_def, "one_ulp_sensitivity_floor": floor, "refinement_steps_gpu": acc_gpu, "refinement_steps_oracle": acc_ref})
     assert res_gpu <= 4.0 * res_ref + 1e-16, (res_gpu, res_ref)
     assert err_r < max(TOL_DY, floor), (err_r, floor)
+    assert err_def < max(TOL_DY, floor), (err_def, floor)
     assert err < 1e-7, err
     g.close()
 

@@ -194,9 +194,10 @@ def test_guarded_refinement_and_linear_solver_config(key, n_steps):
     assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) < TOL_DY
     # max_iters = 0 is the plain solve
     x0, acc0, _ = g.solve_in_place_with_refinement(rhs, 0, 1e-30)
-    assert acc0 == 0 and np.array_equal(x0, g.solve_in_place(rhs))
     # the config routes solve_in_place through the refinement (tol 1e-12, linear_solver.rs:84-101)
-    assert g.get_linear_solver_config() == ("Auto", "ToFaerSparse", 0)
+    assert g.get_linear_solver_config() == ("Auto", "ToFaerSparse", -1)       # -1: library default (one guarded step at size)
+    g.set_linear_solver_config("Auto", "ToFaerSparse", 0)                     # the reference's default: never refine
+    assert acc0 == 0 and np.array_equal(x0, g.solve_in_place(rhs))            # 0 steps configured: the plain solve
     g.set_linear_solver_config("ForceBanded", "Never", 2)
     assert g.get_linear_solver_config() == ("ForceBanded", "Never", 2)
     x2 = g.solve_in_place(rhs)

@@ -272,9 +272,11 @@ def multi_gpu_check(solver, key, spec, n_global, nv, rank, world, local_rank, pe
         info["method"] = "closed form y = x, z = 1 (forward Euler is exact for it)"
     else:
         need_gb = n_global * (6 * nv + 7 * nv * nv) * 8 / 1e9
-        if need_gb > 120.0:
+        have_gb = (n_global // world) * (6 * nv + 7 * nv * nv) * 8 / 1e9      # what rank 0 already holds
+        if need_gb + have_gb > 150.0:
             err = torch.full((1,), float("nan"), device="cuda", dtype=torch.float64)
-            info["method"] = f"skipped: the single-GPU rerun of {n_global} points needs {need_gb:.0f} GB"
+            info["method"] = (f"solution check skipped: the single-GPU rerun of {n_global} points needs {need_gb:.0f} GB next to the "
+                              f"{have_gb:.0f} GB of rank 0's own slab (residual_inf and the multi-GPU parity tests cover this case)")
         else:
             full = torch.empty((n_global + 1) * nv, device="cuda", dtype=torch.float64)
             it1 = torch.zeros(1, device="cuda", dtype=torch.float64)
@@ -610,7 +612,7 @@ def main():
         if world == 1:
             others = [w for w in ("c2", "c5") if w != args.workload]
         else:
-            others = [w for w in ("c4", "c2") if w != args.workload]
+            others = [w for w in ("c4", "c5", "c2") if w != args.workload]   # c5 weak: 2.5e5 points per GPU = 2e6 on 8 GPUs
         for w in others:
             try:
                 r = run_workload(args, w, rank, world, local_rank, primary=False)

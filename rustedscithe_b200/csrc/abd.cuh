@@ -318,8 +318,8 @@ __device__ __forceinline__ void abd_backward_warp(const AbdLevel &L, int64_t war
         double t = 0.0, inv = 1.0;
 #pragma unroll
         for (int c = 0; c < NV; ++c) U[c] = 0.0;
-        if (L.prefetch && slab_ok && i - 1 >= 1) {
-            const char *nx = reinterpret_cast<const char *>(L.UEF + (g - 1) * (int64_t)Pk::UEF);
+        if (L.prefetch && slab_ok && i - L.prefetch >= 1) {   // L.prefetch = distance in block rows
+            const char *nx = reinterpret_cast<const char *>(L.UEF + (g - L.prefetch) * (int64_t)Pk::UEF);
             for (int off = (lane & (G - 1)) * 128; off < Pk::UEF * 8; off += G * 128)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + off));
         }

@@ -408,8 +408,8 @@ __device__ __forceinline__ void abd_forward4_slab(const AbdLevel &L, int64_t sla
     for (int i = 1; i < len; ++i) {
         const int64_t g = g0 + i;
         const double *lt_g = L.Lm + g * (int64_t)Cf::LT;
-        if (L.prefetch && i + 1 < len && lane * 128 < Cf::LT * 8)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(lt_g + Cf::LT) + lane * 128));
+        if (L.prefetch && i + L.prefetch < len && lane * 128 < Cf::LT * 8)   // L.prefetch = distance in block rows
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(lt_g + (int64_t)L.prefetch * Cf::LT) + lane * 128));
         unsigned pword[NB];
 #pragma unroll
         for (int b = 0; b < NB; ++b) pword[b] = pnext[b];

@@ -485,7 +485,10 @@ static int build_level(H *s, LevelBuf *lv, int64_t n, int S, const double *A, co
     k.n = n;
     k.S = S;
     k.nv = nv;
-    k.prefetch = 1;   // measured at nv = 12, 1e6 rows: solve 1.15 -> 1.08 ms; distances 2 / 4 are not better
+    k.prefetch = 1;   // L2 prefetch distance of the sweeps in block rows; measured at nv = 12, 1e6 rows: solve 1.15 -> 1.08 ms, 2 / 4 not better
+    if (const char *e = std::getenv("RST_B200_PREFETCH_MID")) {   // experiment: deeper prefetch on the latency-bound middle levels
+        if (n < 200000) k.prefetch = std::atoi(e) > 0 ? std::atoi(e) : 1;
+    }
     k.nslabs = (n + S - 1) / S;
     k.A = A;
     k.B = B;

@@ -249,6 +249,16 @@ struct BigImpl {
         // the register-tiled DFMA kernel (same factor layout) for the A/B comparison the north star asks for
         if (!v1 && L.nv == BigdCfg::NV && std::getenv("RST_B200_BIG_DFMA") == nullptr && std::getenv("RST_B200_BIG_W32") == nullptr) {
             constexpr int smem = (int)sizeof(BigdSmem);
+            if (std::getenv("RST_B200_BIGD_HYBRID") != nullptr) {   // experiment: 16-warp hybrid (128 registers, warps 0-3 double as panel warps); measured 51.2 vs 49.8 ms
+                if (ident_b) {
+                    cudaFuncSetAttribute(bigh_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    bigh_factor_kernel<true><<<(unsigned)L.nslabs, BigdCfg::THREADS, smem, st>>>(L, flags);
+                } else {
+                    cudaFuncSetAttribute(bigh_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                    bigh_factor_kernel<false><<<(unsigned)L.nslabs, BigdCfg::THREADS, smem, st>>>(L, flags);
+                }
+                return;
+            }
             if (ident_b) {
                 cudaFuncSetAttribute(bigd_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                 bigd_factor_kernel<true><<<(unsigned)L.nslabs, BigdCfg::THREADS + 128, smem, st>>>(L, flags);

@@ -460,6 +460,33 @@ def run_workload(args, workload, rank, world, local_rank, primary):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
         bytes_local = n_local * nv * 8
+        serial_e2e = mult * e2e_iters / (e2e_ms * 1e-3)
+        e2e_steps, pipeline = steps, "off: one handle, copy -> solve -> copy in sequence"
+
+        # ---- the same calls from TWO host threads, each with its own solver handle and stream (N = 1): the PCIe copies of
+        # one solve overlap the kernels of the other.  Every solve still pays its own H2D + D2H inside the timed region.
+        footprint_gb = n_local * (6 * nv + 7 * nv * nv) * 8 / 1e9
+        if world == 1 and not args.no_pipeline and footprint_gb < 40.0:
+            from rustedscithe_b200.pipeline import SolvePipeline
+            pipe = SolvePipeline(key, n_global, DampedSolverOptions.from_spec(spec, device=local_rank, slab=args.slab), lanes=2)
+            guess = pipe.pinned(y0)
+            sols, _ = pipe.solve_many([guess, guess])              # untimed: warm-up and check against the one-handle answer
+            if not all(s_ is not None and np.array_equal(s_, out_np) for s_ in sols):
+                raise SystemExit("pipelined e2e: the lanes did not reproduce the one-handle solution")
+            del sols
+            n_pipe = 2 * max(1, (steps + 1) // 2)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            done, st_pipe = pipe.solve_many([guess] * n_pipe, sink=lambda i, view: None)
+            torch.cuda.synchronize()
+            pipe_ms = (time.perf_counter() - t0) * 1e3
+            if not all(done):
+                raise SystemExit("pipelined e2e: a solve did not converge")
+            e2e_iters, e2e_ms, e2e_steps = sum(s_[1] for s_ in st_pipe), pipe_ms, n_pipe
+            pipeline = ("rustedscithe_b200.pipeline.SolvePipeline, 2 solver handles on 2 host threads: set_state (H2D) -> newton_solve -> "
+                        "get_state (D2H) per solve from / into pinned host vectors; the solves take turns on the GPU (host mutex) "
+                        "while the other handle's copies run; wall clock over all solves, synchronised on both sides")
+            pipe.close()
         # PCIe rate of the two copies alone (same pinned buffers), so the host-side limiter has a name
         barrier()
         tc = time.perf_counter()
@@ -543,6 +570,7 @@ def run_workload(args, workload, rank, world, local_rank, primary):
 
         e2e = {"value": mult * e2e_iters / (e2e_ms * 1e-3), "unit": "iter/s", "h2d_bytes_per_step": bytes_local,
                "d2h_bytes_per_step": bytes_local + 40 * per_solve["linear_solves"],
+               "steps": e2e_steps, "pipeline": pipeline, "one_handle_value": serial_e2e,
                "pcie_copy_ms_per_step": copy_ms, "pcie_gbs_per_rank": 2 * bytes_local / (copy_ms * 1e-3) / 1e9}
         out = {
             "value": value, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
@@ -575,6 +603,7 @@ def main():
     ap.add_argument("--slab", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the compact results of the other configurations")
+    ap.add_argument("--no-pipeline", action="store_true", help="e2e with one solver handle only (no second handle / host thread)")
     ap.add_argument("--nccl-exchange", action="store_true",
                     help="move the interface rows with torch.distributed/NCCL through the host callback instead of the "
                          "NVLink peer-memory kernel")

@@ -284,6 +284,14 @@ int rst_b200_btd_solve_multiple_in_place(rst_b200_btd *s, double *rhs, size_t nr
  * bindings move data to / from rst_b200_device_ptr buffers */
 int rst_b200_memcpy(void *dst, const void *src, size_t bytes, int kind);
 
+/* page-locked host memory for the state vectors a host hands to rst_b200_set_state / rst_b200_get_state: from pinned
+ * buffers the two copies run at the PCIe rate and asynchronously to the kernels of OTHER handles, which is what lets a
+ * host that runs several independent solves (one handle per worker thread, as a Rust host would with rayon over
+ * NRBVP instances, NR_Damp_solver_damped.rs:2130-2156 being one solve) hide the copies of one behind the kernels of
+ * another -- rustedscithe_b200/pipeline.py is that pattern.  Pageable buffers work too, only slower. */
+int rst_b200_host_alloc(size_t bytes, void **out);
+int rst_b200_host_free(void *p);
+
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t rst_b200_launch_count(const rst_b200_solver *s);
 

@@ -249,16 +249,6 @@ struct BigImpl {
         // the register-tiled DFMA kernel (same factor layout) for the A/B comparison the north star asks for
         if (!v1 && L.nv == BigdCfg::NV && std::getenv("RST_B200_BIG_DFMA") == nullptr && std::getenv("RST_B200_BIG_W32") == nullptr) {
             constexpr int smem = (int)sizeof(BigdSmem);
-            if (std::getenv("RST_B200_BIGD_HYBRID") != nullptr) {   // experiment: 16-warp hybrid (128 registers, warps 0-3 double as panel warps); measured 51.2 vs 49.8 ms
-                if (ident_b) {
-                    cudaFuncSetAttribute(bigh_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                    bigh_factor_kernel<true><<<(unsigned)L.nslabs, BigdCfg::THREADS, smem, st>>>(L, flags);
-                } else {
-                    cudaFuncSetAttribute(bigh_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                    bigh_factor_kernel<false><<<(unsigned)L.nslabs, BigdCfg::THREADS, smem, st>>>(L, flags);
-                }
-                return;
-            }
             if (ident_b) {
                 cudaFuncSetAttribute(bigd_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                 bigd_factor_kernel<true><<<(unsigned)L.nslabs, BigdCfg::THREADS + 128, smem, st>>>(L, flags);
@@ -810,14 +800,27 @@ extern "C" int rst_b200_memcpy(void *dst, const void *src, size_t bytes, int kin
     CUDA_TRY(cudaMemcpy(dst, src, bytes, (cudaMemcpyKind)kind));
     return RST_B200_OK;
 }
+extern "C" int rst_b200_host_alloc(size_t bytes, void **out) {
+    if (!out || bytes == 0) return fail(RST_B200_ERR_INVALID, "bad host_alloc arguments");
+    *out = nullptr;
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return RST_B200_OK;
+}
+extern "C" int rst_b200_host_free(void *p) {
+    if (!p) return RST_B200_OK;
+    CUDA_TRY(cudaFreeHost(p));
+    return RST_B200_OK;
+}
 extern "C" int64_t rst_b200_launch_count(const rst_b200_solver *s) { return s ? s->launches : 0; }
 extern "C" int rst_b200_sync(rst_b200_solver *s) {
     if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(s->device));   // the caller may be a fresh worker thread (one handle per thread: pipeline.py)
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return RST_B200_OK;
 }
 extern "C" int rst_b200_set_params(rst_b200_solver *s, const double *params, int n_params) {
     if (!s || n_params != s->np || (n_params > 0 && !params)) return fail(RST_B200_ERR_INVALID, "parameter count mismatch");
+    CUDA_TRY(cudaSetDevice(s->device));
     if (s->np > 0) {
         CUDA_TRY(cudaMemcpyAsync(s->d_params, params, s->np * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1050,6 +1053,7 @@ static inline int64_t reduced_index(const rst_b200_solver *s, int64_t g, int v) 
 // (numeric_discretization.rs:80-106), so every interior node is one contiguous run in both orderings: the state moves
 // with ONE large copy straight between the caller's buffer and HBM plus two nv-sized boundary copies.
 static int move_state(rst_b200_solver *s, double *y, bool to_device) {
+    CUDA_TRY(cudaSetDevice(s->device));
     const int nv = s->nv;
     const int nl = s->layout.nl;
     const int64_t g_lo = s->j_begin, g_hi = s->j_begin + s->n;          // local nodes [g_lo, g_hi]
@@ -1758,6 +1762,7 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
 extern "C" int rst_b200_newton_iterate(rst_b200_solver *s, const rst_b200_newton_opts *o, int recalc,
                                        rst_b200_newton_stats *st) {
     if (!s || !o || !st) return fail(RST_B200_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
     if (recalc || !s->factored) TRY(recalc_jacobian(s, st));
     st->iterations++;
     int status = 0;
@@ -1769,6 +1774,7 @@ extern "C" int rst_b200_newton_iterate(rst_b200_solver *s, const rst_b200_newton
 
 extern "C" int rst_b200_newton_solve(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b200_newton_stats *st) {
     if (!s || !o || !st) return fail(RST_B200_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
     std::memset(st, 0, sizeof(*st));
     const auto t_begin = std::chrono::steady_clock::now();
     bool have_jac = false, recalc = true;

@@ -124,6 +124,8 @@ SYMBOLS = {
     "rst_b200_btd_solve_in_place": (C.c_int, [_H, c_f64_p, C.c_size_t]),
     "rst_b200_btd_solve_multiple_in_place": (C.c_int, [_H, c_f64_p, C.c_size_t, C.c_size_t]),
     "rst_b200_memcpy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "rst_b200_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "rst_b200_host_free": (C.c_int, [C.c_void_p]),
     "rst_b200_launch_count": (C.c_int64, [_H]),
 }
 

@@ -550,3 +550,30 @@ def test_nan_in_the_state_is_reported_not_propagated(key, n_steps):
     g.set_state(spec.guess(n_steps))
     assert g.try_solve() is not None
     g.close()
+
+
+@pytest.mark.gpu
+def test_solve_pipeline_two_lanes_matches_single_handle():
+    """pipeline.SolvePipeline: independent solves spread over two handles / host threads give, bit for bit, what one handle
+    gives for the same guesses (different guesses per solve so that a mixed-up buffer would show)."""
+    from rustedscithe_b200.pipeline import SolvePipeline
+    spec = problems.get("flame12")
+    n = 4000
+    base = np.asarray(spec.guess(n), dtype=np.float64).reshape(-1)
+    rng = np.random.default_rng(5)
+    guesses = [base * (1.0 - 1e-4 * rng.random(base.shape)) for _ in range(6)]
+    one = NRBVP("flame12", None, n, DampedSolverOptions.from_spec(spec))
+    want = []
+    for g in guesses:
+        one.set_state(g)
+        want.append(one.try_solve())
+    iters_one = one.get_statistics()["number of iterations"]
+    one.close()
+    pipe = SolvePipeline("flame12", n, DampedSolverOptions.from_spec(spec), lanes=2)
+    sols, stats = pipe.solve_many(guesses)
+    pipe.close()
+    assert all(st[0] == 1 for st in stats)
+    assert stats[-1][1] == iters_one
+    for w, s in zip(want, sols):
+        assert w is not None and s is not None
+        np.testing.assert_array_equal(np.asarray(w).reshape(-1), s)

@@ -227,6 +227,23 @@ __global__ void __launch_bounds__(256) newton_trial_dev_kernel(const double *__r
         Yt[idx] = Y[idx] - dY[idx] * lambda;
 }
 
+// First trial of an iteration whose undamped step is ALREADY KNOWN: when the previous iteration accepted its first trial
+// (state Yt, step dY1 = J^-1 F(Yt), scalars in slot 1) and the Jacobian is kept, the reference's next iteration recomputes
+// F(y) and J^-1 F(y) at y = Yt with the same factors (NR_Damp_solver_damped.rs:1862-1880) -- bit for bit the trial's dY1.
+// This kernel takes them over instead: dY <- dY1, scalars slot 0 <- slot 1, Yt = Y - lambda dY with lambda = fbound.
+__global__ void __launch_bounds__(256) newton_trial_carry_kernel(const double *__restrict__ Y, const double *__restrict__ dY1,
+                                                                 double *__restrict__ dY, double *__restrict__ Yt,
+                                                                 double *__restrict__ scal, int64_t total) {
+    const double lambda = 1.0 * scal[8 + 2];
+    if (blockIdx.x == 0 && threadIdx.x < 8) scal[threadIdx.x] = scal[8 + threadIdx.x];   // nobody reads slot 0 in this kernel
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const double d = dY1[idx];
+        dY[idx] = d;
+        Yt[idx] = Y[idx] - d * lambda;
+    }
+}
+
 // ---- reduced ordering <-> full node-major state (numeric_discretization.rs:80-106, BVP_utils.rs:534-558) ----
 // reduced index k -> full position: the nl pinned slots of node 0 and the nr pinned slots of node N are deleted
 struct LayoutArgs {

@@ -420,6 +420,7 @@ struct rst_b200_solver {
     // number lives on the device)
     struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0; };
     std::map<uintptr_t, GraphEntry> step_graphs;            // speculative damped step, key = Y buffer
+    std::map<uintptr_t, GraphEntry> carry_graphs;           // the same with the undamped step carried over from the accepted trial
     std::map<uintptr_t, GraphEntry> jac_graphs;             // Jacobian assembly + factorisation of every level
     std::map<uintptr_t, GraphEntry> frozen_graphs;          // frozen-Jacobian iteration, key = Y buffer | refresh flag
 };
@@ -783,7 +784,7 @@ extern "C" void rst_b200_destroy(rst_b200_solver *s) {
     }
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    for (auto *cache : {&s->step_graphs, &s->jac_graphs, &s->frozen_graphs})
+    for (auto *cache : {&s->step_graphs, &s->carry_graphs, &s->jac_graphs, &s->frozen_graphs})
         for (auto &kv : *cache)
             if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (void *p : s->peer_mapped) cudaIpcCloseMemHandle(p);
@@ -1664,8 +1665,13 @@ static void unpack_scalars(const double *h, rst_b200_scalars *sc) {
     sc->sumsq_step = h[0]; sc->tol_sum = h[1]; sc->fbound = h[2]; sc->nan_flag = h[3]; sc->device_flags = h[4];
 }
 
-static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b200_newton_stats *st, int *status) {
+// `carry` (in): the previous iteration accepted its FIRST (speculative) trial and the factors are unchanged, so this
+// iteration's undamped step and its scalars are the trial's (newton_trial_carry_kernel) and are not recomputed.
+// `*first_trial_accepted` (out): this iteration ended that way.
+static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b200_newton_stats *st, int *status, bool carry = false,
+                       bool *first_trial_accepted = nullptr) {
     rst_b200_scalars sc{}, sc1{};
+    if (first_trial_accepted) *first_trial_accepted = false;
     // trial steps go to dY1: the undamped step in dY is re-used by every damping trial (:1934, :1971)
     struct Restore {
         rst_b200_solver *s;
@@ -1674,20 +1680,25 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
     // Device-only exchange (1 GPU, or NVLink mailboxes): the first damping trial uses lambda = fbound, which is already
     // on the device, so undamped step + first trial are enqueued back to back and the host synchronises ONCE.
     const bool speculative = (s->world == 1 || s->p2p_enabled) && o->max_damp_iter > 0;
+    carry = carry && speculative;
     s->scal_slot = 0;
     // The speculative sequence is ~25-45 launches with fixed arguments: small meshes are launch bound, so it is captured
     // into a CUDA graph (per Y / Y_trial parity) the second time it runs and replayed with one launch afterwards.
     const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;   // read per call: tests toggle it
     {
         bool replayed = false;
-        TRY(run_graphed(s, s->step_graphs, (uintptr_t)s->Y, speculative && graphs_on, &replayed, [&]() -> int {
-            TRY(newton_step(s, 0));
-            if (!speculative) return RST_B200_OK;
-            TRY(rst_b200_reduce_local(s, 0));
-            set_solution_buffer(s, s->dY1);
+        TRY(run_graphed(s, carry ? s->carry_graphs : s->step_graphs, (uintptr_t)s->Y, speculative && graphs_on, &replayed, [&]() -> int {
             const int64_t total = (s->n + 1) * (int64_t)s->nv;
-            newton_trial_dev_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY, s->Yt, s->d_scal, total);
+            if (!carry) {
+                TRY(newton_step(s, 0));
+                if (!speculative) return RST_B200_OK;
+                TRY(rst_b200_reduce_local(s, 0));
+                newton_trial_dev_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY, s->Yt, s->d_scal, total);
+            } else {
+                newton_trial_carry_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY1, s->dY, s->Yt, s->d_scal, total);
+            }
             s->launches++;
+            set_solution_buffer(s, s->dY1);
             s->scal_slot = 1;
             TRY(newton_step(s, 1));
             TRY(rst_b200_reduce_local(s, 1));
@@ -1697,7 +1708,8 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
             s->launches++;
             return RST_B200_OK;
         }));
-        st->linear_solves += speculative ? 2 : 1;   // counted here, not in the (possibly captured / replayed) sequence
+        st->linear_solves += speculative ? 2 : 1;   // the reference's count: counted here, not in the (possibly captured / replayed) sequence
+        if (carry) st->solves_reused++;
         if (replayed) {
             s->reduce_ready = 0;
             s->fuse_reduce_state = -1;
@@ -1748,7 +1760,11 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
         s1 = std::sqrt(sc1.sumsq_step);
         conv = sc1.tol_sum > o->abs_tol ? sc1.tol_sum : o->abs_tol;  // convergence_condition, BVP_utils_damped.rs:209-222
         st->last_lambda = lambda;
-        if (s1 < 1.0 || s1 < s0) { accepted = true; break; }      // :1962
+        if (s1 < 1.0 || s1 < s0) {                                // :1962
+            accepted = true;
+            if (first_trial_accepted) *first_trial_accepted = speculative && k == 0;
+            break;
+        }
         lambda = lambda / std::pow(2.0, (double)k + o->damp_factor); // :1971
         k += 1;
     }
@@ -1778,6 +1794,9 @@ extern "C" int rst_b200_newton_solve(rst_b200_solver *s, const rst_b200_newton_o
     std::memset(st, 0, sizeof(*st));
     const auto t_begin = std::chrono::steady_clock::now();
     bool have_jac = false, recalc = true;
+    // carry: the accepted first trial of the previous iteration IS this iteration's undamped step (same y, same factors)
+    static const bool carry_on = std::getenv("RST_B200_NO_CARRY") == nullptr;
+    bool carry = false;
     int m = 0, n_jac_reeval = 0, it = 0, status = 0;
     while (it < o->max_iterations) {
         recalc = (!have_jac || m > o->max_jac) ? true : recalc;   // jac_recalc, BVP_utils_damped.rs:185-207
@@ -1786,15 +1805,19 @@ extern "C" int rst_b200_newton_solve(rst_b200_solver *s, const rst_b200_newton_o
             if (rc != RST_B200_OK) { st->status = rc; return rc; }
             have_jac = true;
             m = 0;
+            carry = false;
         }
         m += 1;
         it += 1;
         st->iterations++;
-        int rc = damped_step(s, o, st, &status);
+        bool first_accepted = false;
+        int rc = damped_step(s, o, st, &status, carry && carry_on, &first_accepted);
+        carry = false;
         if (rc != RST_B200_OK) { st->status = rc; return rc; }
         if (status == 0) {
             TRY(rst_b200_accept_trial(s));
             recalc = false;
+            carry = first_accepted;
         } else if (status == 1) {
             TRY(rst_b200_accept_trial(s));
             break;

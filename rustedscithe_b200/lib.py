@@ -40,7 +40,7 @@ class NewtonStats(C.Structure):
                 ("factorizations", C.c_int), ("last_s0", C.c_double), ("last_s1", C.c_double),
                 ("last_conv", C.c_double), ("last_fbound", C.c_double), ("last_lambda", C.c_double),
                 ("ms_assemble", C.c_double), ("ms_factor", C.c_double), ("ms_solve", C.c_double),
-                ("ms_total", C.c_double)]
+                ("ms_total", C.c_double), ("solves_reused", C.c_int)]
 
 
 class FrozenOpts(C.Structure):

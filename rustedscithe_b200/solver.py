@@ -271,6 +271,7 @@ class NRBVP:
         s = self.stats
         return {"number of iterations": s.iterations, "number of solving linear systems": s.linear_solves,
                 "number of jacobians recalculations": s.jac_recalcs, "factorizations": s.factorizations,
+                "solves reused": s.solves_reused,
                 "number of grid refinements": getattr(self, "grid_refinements", 0),
                 "status": s.status, "ms_total": s.ms_total}
 

@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path (through the C ABI, librst_b200.so) against the CPU oracle on the same
 seeded inputs.  Tolerances are BASELINE.json's: residual / Jacobian entries 1e-12 relative, each linear-solve
 dy 1e-10 relative to the reference banded LU, converged solutions 1e-9 with the same Newton iteration count."""
+import os
+
 import numpy as np
 import pytest
 
@@ -577,3 +579,48 @@ def test_solve_pipeline_two_lanes_matches_single_handle():
     for w, s in zip(want, sols):
         assert w is not None and s is not None
         np.testing.assert_array_equal(np.asarray(w).reshape(-1), s)
+
+
+_CARRY_SCRIPT = r"""
+import json, sys
+import numpy as np
+from rustedscithe_b200 import problems
+from rustedscithe_b200.solver import NRBVP, DampedSolverOptions
+out = {}
+for key, n in (("flame12", 3000), ("linear2", 5000), ("combustion6", 2000), ("coupled64", 300)):
+    spec = problems.get(key)
+    sv = NRBVP(key, spec.guess(n), n, DampedSolverOptions.from_spec(spec))
+    for rep in range(3):      # direct launches, graph capture, graph replay
+        sv.set_state(np.asarray(spec.guess(n), dtype=np.float64).reshape(-1))
+        sol = sv.try_solve()
+    st = sv.get_statistics()
+    out[key] = {"sol": None if sol is None else np.asarray(sol).tobytes().hex(), "it": st["number of iterations"],
+                "ls": st["number of solving linear systems"], "jac": st["number of jacobians recalculations"],
+                "reused": st["solves reused"]}
+    sv.close()
+json.dump(out, open(sys.argv[1], "w"))
+"""
+
+
+@pytest.mark.gpu
+def test_carried_undamped_step_is_bit_identical_to_recomputing_it(tmp_path):
+    """The undamped step taken over from the accepted first trial (newton_trial_carry_kernel) against recomputing it
+    (RST_B200_NO_CARRY=1, the reference's sequence): same bits in the converged state, same counters; and the carry is
+    actually taken on the multi-iteration problems."""
+    import json
+    import subprocess
+    import sys
+    res = {}
+    for tag, env_extra in (("carry", {}), ("recompute", {"RST_B200_NO_CARRY": "1"})):
+        env = {k: v for k, v in os.environ.items() if k != "RST_B200_NO_CARRY"}
+        env.update(env_extra)
+        path = tmp_path / f"{tag}.json"
+        subprocess.run([sys.executable, "-c", _CARRY_SCRIPT, str(path)], check=True, env=env,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        res[tag] = json.load(open(path))
+    for key in res["carry"]:
+        a, b = res["carry"][key], res["recompute"][key]
+        assert a["sol"] is not None and a["sol"] == b["sol"], key
+        assert (a["it"], a["ls"], a["jac"]) == (b["it"], b["ls"], b["jac"]), key
+        assert b["reused"] == 0
+    assert res["carry"]["flame12"]["reused"] >= 1

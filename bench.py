@@ -436,7 +436,7 @@ def run_workload(args, workload, rank, world, local_rank, primary):
         host_y = torch.from_numpy(y0.copy()).pin_memory()
         host_np = host_y.numpy()
         ptr = host_np.ctypes.data_as(C.POINTER(C.c_double))
-        host_out = torch.empty_like(host_y).pin_memory()
+        host_out = torch.zeros_like(host_y).pin_memory()
         out_np = host_out.numpy()
         optr = out_np.ctypes.data_as(C.POINTER(C.c_double))
 
@@ -468,26 +468,36 @@ def run_workload(args, workload, rank, world, local_rank, primary):
         # ---- the same calls from TWO host threads, each with its own solver handle and stream (N = 1): the PCIe copies of
         # one solve overlap the kernels of the other.  Every solve still pays its own H2D + D2H inside the timed region.
         footprint_gb = n_local * (6 * nv + 7 * nv * nv) * 8 / 1e9
-        if world == 1 and not args.no_pipeline and footprint_gb < 40.0:
+        if not args.no_pipeline and footprint_gb < 40.0 and (world == 1 or not args.nccl_exchange):
             from rustedscithe_b200.pipeline import SolvePipeline
-            pipe = SolvePipeline(key, n_global, DampedSolverOptions.from_spec(spec, device=local_rank, slab=args.slab), lanes=2)
+            pipe = SolvePipeline(key, n_global, DampedSolverOptions.from_spec(spec, device=local_rank, rank=rank, world=world,
+                                                                              slab=args.slab), lanes=2)
+            if world > 1:       # every lane has its own NVLink mailboxes: wire lane k to the peers' lane k
+                for sv in pipe.solvers:
+                    handles = [None] * world
+                    dist.all_gather_object(handles, sv.p2p_handle())
+                    sv.p2p_open(handles)
+                dist.barrier()
             guess = pipe.pinned(y0)
             sols, _ = pipe.solve_many([guess, guess])              # untimed: warm-up and check against the one-handle answer
             if not all(s_ is not None and np.array_equal(s_, out_np) for s_ in sols):
                 raise SystemExit("pipelined e2e: the lanes did not reproduce the one-handle solution")
             del sols
             n_pipe = 2 * max(1, (steps + 1) // 2)
-            torch.cuda.synchronize()
+            barrier()
             t0 = time.perf_counter()
             done, st_pipe = pipe.solve_many([guess] * n_pipe, sink=lambda i, view: None)
-            torch.cuda.synchronize()
+            barrier()
             pipe_ms = (time.perf_counter() - t0) * 1e3
             if not all(done):
                 raise SystemExit("pipelined e2e: a solve did not converge")
-            e2e_iters, e2e_ms, e2e_steps = sum(s_[1] for s_ in st_pipe), pipe_ms, n_pipe
-            pipeline = ("rustedscithe_b200.pipeline.SolvePipeline, 2 solver handles on 2 host threads: set_state (H2D) -> newton_solve -> "
-                        "get_state (D2H) per solve from / into pinned host vectors; the solves take turns on the GPU (host mutex) "
-                        "while the other handle's copies run; wall clock over all solves, synchronised on both sides")
+            t = torch.tensor([pipe_ms], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_iters, e2e_ms, e2e_steps = sum(s_[1] for s_ in st_pipe), float(t.item()), n_pipe
+            pipeline = ("rustedscithe_b200.pipeline.SolvePipeline, 2 solver handles on 2 host threads per rank: set_state (H2D) -> "
+                        "newton_solve -> get_state (D2H) per solve from / into pinned host vectors; the solves take turns on the GPU "
+                        "(fixed order) while the other handle's copies run; wall clock over all solves, barrier + synchronise on both sides")
             pipe.close()
         # PCIe rate of the two copies alone (same pinned buffers), so the host-side limiter has a name
         barrier()

@@ -7,7 +7,7 @@ next to 10.9 ms of kernels).  A host with MANY solves to do -- a sweep over para
 a continuation -- runs them on several handles, one worker thread each (the reference side of that is a thread pool over
 NRBVP instances); the library's handles are independent (own stream, own buffers, no shared mutable state), so the copies of
 one handle overlap the kernels of another.  This module is that pattern, nothing more: `lanes` handles, one thread per lane,
-and a host mutex that lets one solve compute at a time so the lanes fall into copy / compute alternation instead of
+and a turn order (solve i computes after solve i - 1) so the lanes fall into copy / compute alternation instead of
 contending for the SMs.  Every solve still pays its own H2D and D2H.
 """
 from __future__ import annotations
@@ -30,6 +30,7 @@ class PinnedVector:
         _lib.check(L.rst_b200_host_alloc(int(n) * 8, C.byref(self._p)), L)
         self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_double)), shape=(int(n),))
         self.ptr = C.cast(self._p, _lib.c_f64_p)
+        self.array[:] = 0.0      # world > 1: get_state writes only the nodes this rank owns
 
     def free(self):
         if self._p:
@@ -55,7 +56,6 @@ class SolvePipeline:
         self.L, self.n = s0.L, s0.n
         self._in = [PinnedVector(self.L, self.n) for _ in range(lanes)]
         self._out = [PinnedVector(self.L, self.n) for _ in range(lanes)]
-        self._turn = threading.Lock()
 
     def pinned(self, values=None) -> PinnedVector:
         """A page-locked vector of the state length (optionally filled): guesses kept in these skip the staging copy."""
@@ -77,20 +77,20 @@ class SolvePipeline:
         (as NRBVP.try_solve), stats[i] = (status, iterations, linear_solves, jac_recalcs).  With `sink(i, view)` the
         converged state is handed over as a view of the lane's pinned buffer instead of being copied into a new array."""
         m = len(guesses)
+        lanes = len(self.solvers)
         sols, stats, errors = [None] * m, [None] * m, []
-        nxt = iter(range(m))
-        pick = threading.Lock()
+        # Solve i runs on lane i % lanes and the solves take the GPU in the order 0, 1, 2, ...: deterministic, and with
+        # world > 1 every rank issues the exchanges of its lanes in the same order (a free-for-all could leave two ranks
+        # waiting for each other's OTHER lane).
+        turn = threading.Condition()
+        state = {"next": 0}
 
         def lane(k):
             sv, hin, hout = self.solvers[k], self._in[k], self._out[k]
             L = self.L
             try:
                 _lib.check(L.rst_b200_sync(sv.handle), L)          # binds the worker thread to the handle's device
-                while True:
-                    with pick:
-                        i = next(nxt, None)
-                    if i is None:
-                        return
+                for i in range(k, m, lanes):
                     g = guesses[i]
                     if isinstance(g, PinnedVector):     # the host already keeps this guess in page-locked memory
                         src = g.ptr
@@ -101,8 +101,16 @@ class SolvePipeline:
                         sv.set_params(params[i])
                     _lib.check(L.rst_b200_set_state(sv.handle, src, self.n), L)
                     opts = sv._opts()
-                    with self._turn:
+                    with turn:
+                        turn.wait_for(lambda: state["next"] == i or errors)
+                        if errors:
+                            return
+                    try:
                         _lib.check(L.rst_b200_newton_solve(sv.handle, C.byref(opts), C.byref(sv.stats)), L)
+                    finally:
+                        with turn:
+                            state["next"] = i + 1
+                            turn.notify_all()
                     st = sv.stats
                     stats[i] = (st.status, st.iterations, st.linear_solves, st.jac_recalcs)
                     if st.status == 1:
@@ -113,9 +121,11 @@ class SolvePipeline:
                         else:
                             sols[i] = hout.array.copy()
             except Exception as exc:        # re-raised on the calling thread
-                errors.append(exc)
+                with turn:
+                    errors.append(exc)
+                    turn.notify_all()
 
-        threads = [threading.Thread(target=lane, args=(k,)) for k in range(len(self.solvers))]
+        threads = [threading.Thread(target=lane, args=(k,)) for k in range(lanes)]
         for t in threads:
             t.start()
         for t in threads:

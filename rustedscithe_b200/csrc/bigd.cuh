@@ -19,13 +19,13 @@
 //     rows are transposed through shared memory into UEF [c][k] with coalesced stores.
 // Block sizes other than 64 keep bigr_factor_kernel.
 //
-// Where the time goes (clock64 instrumentation behind BIGD_TIMING, profiles/r02_summary.md): per block of 4 pivots the update
-// warps need ~320 cycles for the hand-over (post pivot rows, look-ahead tile, post panel) and 1 150 - 3 700 cycles for their
-// DMMAs (the B-fragment LDS -> DMMA pairs cannot be prefetched: 96 registers = the accumulator tiles), the panel warps
-// ~3 600 - 4 800 cycles for the 4 pivots: their chain of ~8 dependent FP64 operations per pivot (reciprocal, multiplier,
-// update of the next column) queues behind the update warps' DMMAs in the one FP64 pipe of each scheduler.  A 16-warp
-// hybrid (bigh_factor_kernel: warps 0-3 own tiles AND factor the panel, 128 registers, no spills) measures the same
-// (51.2 vs 49.8 ms): the panel chain, not the registers, is the limit.
+// Where the time goes (tools/bigd_probe.cu = this kernel with the BIGD_X_* / BIGD_NO_DMMA / BIGD_PW1 what-if switches below,
+// tools/coissue_bench.cu, profiles/r02_coissue.md): time = 20 + 3.6 per pivot round + 17.5 ms for the trailing DMMAs at C5's
+// size, exactly additive -- the look-ahead does NOT overlap, because a scheduler's one FP64 pipe serves DMMA before DFMA: a
+// dependent DFMA takes 8 cycles alone, 61 next to one DMMA-streaming warp and is starved next to four, so the panel warps'
+// first FP64 instruction waits for the update warps of their scheduler to finish the block.  All panel warps on one
+// scheduler (BIGD_X_PANEL_ONE_SCHEDULER, 52.7 ms), one panel warp with 4 rows per lane there (BIGD_PW1, 58.2 ms), a 16-warp
+// hybrid at 128 registers (51.2 ms) and an instruction-lean chain (this version) all measure the same or worse.
 #pragma once
 #include "abd4.cuh"
 #include "big.cuh"
@@ -90,10 +90,17 @@ __device__ __forceinline__ void bigd_panel_block(BigdSmem &sm, const AbdLevel &L
     //    multipliers  l = a[ii] / pi  are scale free -- they are formed after the four pivots.  2 FP64 instructions per column.
     //  * the warp-uniform values of the block (4 reciprocals, the 6 entries of L11) are computed ONCE, spread over 10 lanes,
     //    and broadcast by shuffles: 5 FP64 instructions instead of 26.
+#ifdef BIGD_X_SHORTPANEL   // what-if: one pivot round instead of four (wrong numbers, timing only)
+    constexpr int NPIV = 1;
+    double piv[4] = {1.0, 1.0, 1.0, 1.0};
+    double num[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#else
+    constexpr int NPIV = 4;
     double piv[4];            // pivot values (in the block's running scale)
     double num[6];            // entries of the later pivot rows under the earlier pivots: n_ij = num / piv[j]
+#endif
 #pragma unroll
-    for (int ii = 0; ii < 4; ++ii) {
+    for (int ii = 0; ii < NPIV; ++ii) {
         // key = (high word of |a| with its low 7 bits replaced by 127 - row) + 1: threshold pivoting (2^-13
         // relative), ties to the lowest row.  Every warp publishes its best row speculatively: ONE barrier per pivot.
         const unsigned hw = (unsigned)__double2hiint(a[ii]) & 0x7fffffffu;
@@ -196,6 +203,104 @@ __device__ __forceinline__ void bigd_panel_block(BigdSmem &sm, const AbdLevel &L
     BIGD_TICK(4)
 }
 
+// The same block of 4 pivots factored by ONE warp, 4 panel rows per lane (row = lane + 32 j): no barrier and no shared-memory
+// round trip inside -- arg-max = per-lane maximum over 4 rows + one REDUX, pivot row = 4 shuffles.  Same arithmetic, bit for bit.
+__device__ __forceinline__ void bigd_panel_block_w1(BigdSmem &sm, const AbdLevel &L, int64_t g, int b, int lane, unsigned &candbits,
+                                                    unsigned &bad) {
+    constexpr int NV = BigdCfg::NV, R2 = BigdCfg::R2;
+    double a[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a[j][c] = sm.pan[(c >> 1) | ((c & 1) << 1)][lane + 32 * j];
+    const unsigned cand0 = candbits;
+    int whj[4] = {4, 4, 4, 4};
+    double piv[4], num[6];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+        unsigned kbest = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned hw = (unsigned)__double2hiint(a[j][ii]) & 0x7fffffffu;
+            const unsigned key = ((candbits >> j) & 1u) ? (((hw & ~127u) | (unsigned)(127 - (lane + 32 * j))) + 1u) : 0u;
+            kbest = max(kbest, key);
+        }
+        const unsigned mx = __reduce_max_sync(RST_FULL_MASK, kbest);
+        bad |= (mx <= 128u || mx > 0x7ff00000u) ? 1u : 0u;
+        const int prow = 127 - (int)((mx - 1u) & 127u);
+        const int lp = prow & 31, jp = prow >> 5;      // warp-uniform
+        double ap[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double r = a[0][c];
+            r = jp == 1 ? a[1][c] : r;
+            r = jp == 2 ? a[2][c] : r;
+            r = jp == 3 ? a[3][c] : r;
+            ap[c] = __shfl_sync(RST_FULL_MASK, r, lp);
+        }
+        piv[ii] = ap[ii];
+        if (ii == 1) { num[0] = ap[0]; }
+        if (ii == 2) { num[1] = ap[0]; num[2] = ap[1]; }
+        if (ii == 3) { num[3] = ap[0]; num[4] = ap[1]; num[5] = ap[2]; }
+        if (ii < 3) {
+            const int phi = __double2hiint(ap[ii]);
+            const int ex = (phi >> 20) & 0x7ff;
+            const int d = ex != 0 ? 1023 - ex : 0;
+            const double pis = __hiloint2double(ex != 0 ? ((phi & 0x800fffff) | 0x3ff00000) : phi, __double2loint(ap[ii]));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool upd = ((candbits >> j) & 1u) && !((lane == lp) && (jp == j));
+                const int ahi = __double2hiint(a[j][ii]);
+                const int ae = (ahi >> 20) & 0x7ff;
+                const bool ok = ae != 0 && ae + d > 0;
+                const double ais = __hiloint2double(ok ? ahi + d * (1 << 20) : (ahi & (int)0x80000000), ok ? __double2loint(a[j][ii]) : 0);
+                if (upd) {
+#pragma unroll
+                    for (int c = ii + 1; c < 4; ++c) a[j][c] = fma(-ais, ap[c], pis * a[j][c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if ((lane == lp) && (jp == j)) whj[j] = ii;
+        if (lane == lp) candbits &= ~(1u << jp);
+    }
+    double n10, n20, n21, n30, n31, n32, rinv[4];
+    {
+        const int jk = (int)((0x3210210100ull >> (4 * (lane < 10 ? lane : 0))) & 3ull);
+        double pj = piv[0];
+        pj = jk == 1 ? piv[1] : pj; pj = jk == 2 ? piv[2] : pj; pj = jk == 3 ? piv[3] : pj;
+        double nk = 1.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) nk = lane == k ? num[k] : nk;
+        const double v = fast_rcp(pj) * nk;
+        n10 = __shfl_sync(RST_FULL_MASK, v, 0); n20 = __shfl_sync(RST_FULL_MASK, v, 1); n21 = __shfl_sync(RST_FULL_MASK, v, 2);
+        n30 = __shfl_sync(RST_FULL_MASK, v, 3); n31 = __shfl_sync(RST_FULL_MASK, v, 4); n32 = __shfl_sync(RST_FULL_MASK, v, 5);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rinv[j] = __shfl_sync(RST_FULL_MASK, v, 6 + j);
+    }
+    const double i20 = fma(n21, n10, -n20);
+    const double i31 = fma(n32, n21, -n31);
+    const double i30 = fma(-n32, i20, fma(n31, n10, -n30));
+    double *lm = L.Lm + g * (int64_t)(NV * R2) + (int64_t)(4 * b) * R2 + lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = lane + 32 * j;
+        const int lim = ((cand0 >> j) & 1u) ? whj[j] : 0;
+        const double l0 = lim > 0 ? a[j][0] * rinv[0] : 0.0, l1 = lim > 1 ? a[j][1] * rinv[1] : 0.0,
+                     l2 = lim > 2 ? a[j][2] * rinv[2] : 0.0, l3 = lim > 3 ? a[j][3] * rinv[3] : 0.0;
+        const double nt3 = __hiloint2double(__double2hiint(l3) ^ (int)0x80000000, __double2loint(l3));
+        const double nt2 = fma(l3, n32, -l2);
+        const double nt1 = fma(-l3, i31, fma(l2, n21, -l1));
+        const double nt0 = fma(-l3, i30, fma(-l2, i20, fma(l1, n10, -l0)));
+        *reinterpret_cast<double2 *>(&sm.lb[0][2 * r]) = make_double2(nt0, nt1);
+        *reinterpret_cast<double2 *>(&sm.lb[1][2 * r]) = make_double2(nt2, nt3);
+        sm.wh[r] = (unsigned char)whj[j];
+        if (whj[j] < 4) sm.pv[r] = (signed char)(4 * b + whj[j]);
+        st_cs(lm + 32 * j, l0); st_cs(lm + R2 + 32 * j, l1); st_cs(lm + 2 * R2 + 32 * j, l2); st_cs(lm + 3 * R2 + 32 * j, l3);
+    }
+}
+
 // 16 update warps (accumulator tiles) + 4 panel warps (one panel row per lane).  Five warps per scheduler cap the kernel
 // at 96 registers per thread -- exactly the 24 tiles of an update warp; the panel warps need 8.
 template <bool IDENT_B>
@@ -203,11 +308,21 @@ __global__ void __launch_bounds__(BigdCfg::THREADS + 128, 1) bigd_factor_kernel(
     using C = BigdCfg;
     constexpr int NV = C::NV, R2 = C::R2, CT = C::CT, NB = C::NB;
     constexpr int MT = NV / 8;   // column tiles per part: M = tiles 0..7, P = 8..15, Q = 16..23
+#ifdef BIGD_PW1
+    constexpr int ALL = C::THREADS + 32, UPD = C::THREADS;    // barriers 1 / 2
+#else
     constexpr int ALL = C::THREADS + 128, UPD = C::THREADS;   // barriers 1 / 2 (3: among the four panel warps)
+#endif
     extern __shared__ __align__(16) unsigned char bigd_smem_raw[];
     BigdSmem &sm = *reinterpret_cast<BigdSmem *>(bigd_smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#ifndef BIGD_X_PANEL_ONE_SCHEDULER
+#if defined(BIGD_PW1)
+    // ONE panel warp (4 rows per lane) alone with one update warp on scheduler 0: hardware warp 0 = panel, 4 / 8 / 12 retire at
+    // once, the other sixteen are the update warps (5 on each of the schedulers 1-3, 1 on scheduler 0).
+    if (wid == 4 || wid == 8 || wid == 12) return;
+    const bool is_pan = wid == 0;
+    const int warp = is_pan ? 0 : (wid < 16 ? wid - (wid >> 2) - 1 : wid - 4);
+#elif !defined(BIGD_X_PANEL_ONE_SCHEDULER)
     // one panel warp per scheduler: hardware warps 16..19
     const bool is_pan = wid >= C::WARPS;
     const int warp = is_pan ? wid - C::WARPS : wid;
@@ -233,6 +348,7 @@ __global__ void __launch_bounds__(BigdCfg::THREADS + 128, 1) bigd_factor_kernel(
         for (int istep = 1; istep < len; ++istep) {
             const int64_t g = g0 + istep;
             bool cand = true;               // my row has not been pivoted in this block row
+            unsigned candbits = 0xFu;       // BIGD_PW1: bit j = row lane + 32 j has not been pivoted
 #pragma unroll 1
             for (int b = 0; b < NB; ++b) {
 #ifdef BIGD_TIMING
@@ -245,6 +361,8 @@ __global__ void __launch_bounds__(BigdCfg::THREADS + 128, 1) bigd_factor_kernel(
 #ifdef BIGD_TIMING
                 bigd_panel_block(sm, L, g, b, pw, lane, cand, bad, tseg);
                 t_wait += tp1 - tp0; t_lu += clock64() - tp1;
+#elif defined(BIGD_PW1)
+                bigd_panel_block_w1(sm, L, g, b, lane, candbits, bad);
 #else
                 bigd_panel_block(sm, L, g, b, pw, lane, cand, bad);
 #endif

@@ -99,8 +99,11 @@ struct Abd4Smem {
     int pv[Cf::R2];                     // pivot index of each slot in the current block row
 };
 
+#ifndef ABD4_MIN_BLOCKS
+#define ABD4_MIN_BLOCKS 4
+#endif
 template <int NV, bool IDENT_B>
-__global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigned *flags) {
+__global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLevel L, unsigned *flags) {
     using Cf = Abd4Cfg<NV>;
     using Pk = AbdPack<NV>;
     using Sm = Abd4Smem<NV, IDENT_B>;
@@ -258,9 +261,99 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
             const bool cand_at_start = cand;
             int mypiv = 4;                  // 0..3: my slot became pivot `mypiv` of this block
             int ps[4];
-            double n10 = 0.0, n20 = 0.0, n21 = 0.0, n30 = 0.0, n31 = 0.0, n32 = 0.0;   // strict lower triangle of the block
+#ifdef ABD4_X_DIVFREE
+            // what-if (tools/abd4_probe.cu), measured SLOWER here (2.35 vs 1.98 ms: this kernel is bound by instruction and
+            // shared-memory-pipe throughput, and the exponent arithmetic + 20 shuffles cost more than the shorter FP64 chain saves).
+            // DIVISION-FREE elimination inside the block (as bigd.cuh): live rows are updated as
+            //   a'[c] = (pi s) a[c] - (a[ii] s) ap[c]
+            // with pi the pivot and s the power of two that brings pi into [1, 2), applied through the exponent field on the
+            // integer pipe: the per-pivot chain has 2 dependent FP64 operations instead of 6 (reciprocal, multiplier, update),
+            // which matters because co-resident warps stream DMMAs (profiles/r02_coissue.md: a dependent DFMA next to a DMMA stream
+            // takes 61 cycles, not 8).  Every live row carries the same factor, so the arg-max is unchanged; the multipliers
+            // l = a[j] / piv[j] are scale free and are formed after the four pivots, reciprocals and L11 entries once per block,
+            // spread over 10 lanes.
+            double piv[4], num[6];
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
+                const unsigned hw = (unsigned)__double2hiint(a[ii]) & 0x7fffffffu;
+                const unsigned key = cand ? (((hw & ~31u) | (unsigned)(31 - lane)) + 1u) : 0u;
+                const unsigned mx = __reduce_max_sync(RST_FULL_MASK, key);
+                const int p = 31 - (int)((mx - 1u) & 31u);
+                ps[ii] = p;
+                if (lane == p) {
+                    *reinterpret_cast<double2 *>(pr + 4 * ii) = make_double2(a[0], a[1]);
+                    *reinterpret_cast<double2 *>(pr + 4 * ii + 2) = make_double2(a[2], a[3]);
+                }
+                __syncwarp();
+                double ap[4];
+                {
+                    const double2 r0 = *reinterpret_cast<const double2 *>(pr + 4 * ii);
+                    const double2 r1 = *reinterpret_cast<const double2 *>(pr + 4 * ii + 2);
+                    ap[0] = r0.x; ap[1] = r0.y; ap[2] = r1.x; ap[3] = r1.y;
+                }
+                piv[ii] = ap[ii];
+                if (ii == 1) { num[0] = ap[0]; }
+                if (ii == 2) { num[1] = ap[0]; num[2] = ap[1]; }
+                if (ii == 3) { num[3] = ap[0]; num[4] = ap[1]; num[5] = ap[2]; }
+                bad |= (mx <= 32u || mx > 0x7ff00000u) ? 1u : 0u;   // zero / denormal or non-finite pivot
+                const bool is_piv = lane == p;
+                const bool upd = cand && !is_piv;
+                if (ii < 3) {
+                    const int phi = __double2hiint(ap[ii]);
+                    const int ex = (phi >> 20) & 0x7ff;
+                    const int d = ex != 0 ? 1023 - ex : 0;
+                    const double pis = __hiloint2double(ex != 0 ? ((phi & 0x800fffff) | 0x3ff00000) : phi, __double2loint(ap[ii]));
+                    const int ahi = __double2hiint(a[ii]);
+                    const int ae = (ahi >> 20) & 0x7ff;
+                    const bool ok = ae != 0 && ae + d > 0;
+                    const double ais = __hiloint2double(ok ? ahi + d * (1 << 20) : (ahi & (int)0x80000000), ok ? __double2loint(a[ii]) : 0);
+                    if (upd) {
+#pragma unroll
+                        for (int j = ii + 1; j < 4; ++j) a[j] = fma(-ais, ap[j], pis * a[j]);
+                    }
+                }
+                if (is_piv) { mypiv = ii; pv = 4 * b + ii; cand = false; }
+                cand_mask &= ~(1u << p);
+            }
+            pword[b] = (unsigned)ps[0] | ((unsigned)ps[1] << 8) | ((unsigned)ps[2] << 16) | ((unsigned)ps[3] << 24);
+            // warp-uniform values, one per lane: lanes 0..5  n_k = num[k] / piv[j(k)]  (j = 0 0 1 0 1 2), lanes 6..9  1 / piv[lane - 6]
+            double n10, n20, n21, n30, n31, n32, rinv[4];
+            {
+                const int jk = (int)((0x3210210100ull >> (4 * (lane < 10 ? lane : 0))) & 3ull);
+                double pj = piv[0];
+                pj = jk == 1 ? piv[1] : pj; pj = jk == 2 ? piv[2] : pj; pj = jk == 3 ? piv[3] : pj;
+                double nk = 1.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) nk = lane == k ? num[k] : nk;
+                const double v = fast_rcp(pj) * nk;
+                n10 = __shfl_sync(RST_FULL_MASK, v, 0); n20 = __shfl_sync(RST_FULL_MASK, v, 1); n21 = __shfl_sync(RST_FULL_MASK, v, 2);
+                n30 = __shfl_sync(RST_FULL_MASK, v, 3); n31 = __shfl_sync(RST_FULL_MASK, v, 4); n32 = __shfl_sync(RST_FULL_MASK, v, 5);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rinv[j] = __shfl_sync(RST_FULL_MASK, v, 6 + j);
+            }
+            // multipliers of my slot: candidates keep all four, pivot ii keeps those of the earlier pivots, others none
+            const int lim = cand_at_start ? mypiv : 0;
+            const double l0 = lim > 0 ? a[0] * rinv[0] : 0.0, l1 = lim > 1 ? a[1] * rinv[1] : 0.0, l2 = lim > 2 ? a[2] * rinv[2] : 0.0,
+                         l3 = lim > 3 ? a[3] * rinv[3] : 0.0;
+            // (c) inverse of the block's unit lower triangle: i10 = -n10, i21 = -n21, i32 = -n32 through operand negation
+            const double i20 = fma(n21, n10, -n20);
+            const double i31 = fma(n32, n21, -n31);
+            const double i30 = fma(-n32, i20, fma(n31, n10, -n30));
+            // Lt = L * L11^-1
+            const double t3 = l3;
+            const double t2 = fma(-l3, n32, l2);
+            const double t1 = fma(l3, i31, fma(-l2, n21, l1));
+            const double t0 = fma(l3, i30, fma(l2, i20, fma(-l1, n10, l0)));
+#else
+            double n10 = 0.0, n20 = 0.0, n21 = 0.0, n30 = 0.0, n31 = 0.0, n32 = 0.0;   // strict lower triangle of the block
+#ifdef ABD4_X_SHORTPANEL
+            ps[1] = 1; ps[2] = 2; ps[3] = 3;
+#pragma unroll
+            for (int ii = 0; ii < 1; ++ii) {
+#else
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+#endif
                 // arg-max of |a[ii]| over the candidates: ONE 32-bit REDUX on (high word of |a| with its low 5 bits replaced
                 // by 31 - lane): ties and values equal in their leading 15 mantissa bits resolve to the lowest slot
                 const unsigned hw = (unsigned)__double2hiint(a[ii]) & 0x7fffffffu;
@@ -309,23 +402,28 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
             const double t2 = fma(l3, i32, l2);
             const double t1 = fma(l3, i31, fma(l2, i21, l1));
             const double t0 = fma(l3, i30, fma(l2, i20, fma(l1, i10, l0)));
+#endif
             // (d) Lt: shared memory (A fragments) + HBM (forward sweep)
             if (lane < R2) {
                 *reinterpret_cast<double2 *>(lb + lane * 2) = make_double2(-t0, -t1);
                 *reinterpret_cast<double2 *>(lb + 2 * R2 + 8 + lane * 2) = make_double2(-t2, -t3);
                 if (b == NB - 1) pvs[lane] = pv;
             }
+#ifndef ABD4_X_NOLTSTORE
             if (cand_at_start) {
                 const int ncand = R2 - 4 * b;
                 double *dst = lt_g + Cf::lt_off(b) + __popc(cand0 & lanes_below(lane));
                 st_cs(dst, t0); st_cs(dst + ncand, t1); st_cs(dst + 2 * ncand, t2); st_cs(dst + 3 * ncand, t3);
             }
+#endif
             // (e) raw rows of the block's 4 pivots -> shared memory (B fragments); which pivot my slot is comes from its lane
 #pragma unroll
             for (int T = 0; T < RT; ++T) {
                 const int which = __shfl_sync(RST_FULL_MASK, mypiv, 8 * T + gid);
 #pragma unroll
+#ifndef ABD4_X_NOPOST
                 for (int TC = TCB; TC < CT; ++TC) sts128_if(which < 4, xs + which * PITCH + 8 * TC + 2 * q, X[T][TC]);
+#endif
             }
             __syncwarp();
             // (f): X <- X - Lt * X[pivot rows] on the FP64 tensor cores
@@ -335,8 +433,12 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
 #pragma unroll
             for (int TC = TCB; TC < CT; ++TC) {
                 const double bf = xs[q * PITCH + 8 * TC + gid];
+#ifndef ABD4_X_NODMMA   // what-if switch of tools/abd4_probe.cu
 #pragma unroll
                 for (int T = 0; T < RT; ++T) dmma_m8n8k4(X[T][TC], af[T], bf);
+#else
+                X[0][TC].x += bf * af[0] == 123.0 ? 1.0 : 0.0;
+#endif
             }
             __syncwarp();   // xs / lb / pan are rewritten by the next block (or the write-out below)
         }
@@ -347,6 +449,7 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
             for (int b = 1; b < NB; ++b) w = (lane == b) ? pword[b] : w;
             reinterpret_cast<unsigned *>(L.piv + g * (int64_t)Cf::PIV_STRIDE)[lane] = w;
         }
+#ifndef ABD4_X_NOWRITE
 #pragma unroll
         for (int T = 0; T < RT; ++T) {      // final pivot rows, ordered by pivot index
             const int k = pvs[8 * T + gid];
@@ -364,6 +467,7 @@ __global__ void __launch_bounds__(128, 4) abd_factor4_kernel(AbdLevel L, unsigne
                 if (32 * m + 31 < Pk::UEF || lane + 32 * m < Pk::UEF) st_cs(uef + 32 * m, v);
             }
         }
+#endif
         carrymask = cand_mask;
         // (the next block row's first __syncwarp orders these xs reads before its writes)
     }

@@ -534,6 +534,9 @@ def run_workload(args, workload, rank, world, local_rank, primary):
             solver.eval_jacobian(0)
             phases["factor"] = time_phase(lambda: solver.factor(), reps)
             phases["solve"] = time_phase(lambda: solver.solve(), reps)
+            # what the Newton loop runs after a new Jacobian: factorisation + first solve in one call (nv = 12: the right-hand
+            # side rides through the factorisation, no forward sweeps)
+            phases["factor_solve"] = time_phase(lambda: solver.factor_solve(), reps)
             if primary and world == 1:
                 # adaptive-grid hand-off on the current state (marks + scan + refined mesh + interpolated state, all on the device)
                 regrid_ms = time_phase(lambda: solver.new_grid("Pearson", (1e-3, 1.4), fetch=False), 3)
@@ -542,19 +545,23 @@ def run_workload(args, workload, rank, world, local_rank, primary):
         alg = {  # algorithmic bytes per interval, SURVEY.md section 8(d)
             "assemble_FJ": 8 * (2 * nv + nv * nv), "assemble_F": 8 * 2 * nv,
             "factor": 8 * 3 * nv * nv, "solve": 8 * (2 * nv * nv + 2 * nv),
+            "factor_solve": 8 * 3 * nv * nv + 8 * (2 * nv * nv + 2 * nv),
         }
         roofline, kernels = None, {}
         if phases:
             traffic_tab = _ncu_traffic().get(key, {})
             for k, v in phases.items():
                 gbs = alg[k] * n_local / (v * 1e-3) / 1e9
-                tr = traffic_tab.get(k)
+                tr = traffic_tab.get(k) if k != "factor_solve" else None
                 kernels[k] = {"ms": v, "alg_bytes_per_interval": alg[k], "achieved_gbs": gbs, "frac": gbs / peak,
                               "traffic_bytes_per_interval": tr["bytes_per_interval"] if tr else None}
+            # per Newton solve: every factorisation runs as factor_solve (= the factorisation + the first linear solve after it);
+            # the part of it beyond the plain factorisation is booked under "solve"
+            nf, nx = per_solve["factorizations"], per_solve["linear_solves_executed"]
             share = {"assemble_FJ": per_solve["jac_recalcs"] * phases["assemble_FJ"],
-                     "factor": per_solve["factorizations"] * phases["factor"],
-                     "assemble_F": per_solve["linear_solves_executed"] * phases["assemble_F"],
-                     "solve": per_solve["linear_solves_executed"] * phases["solve"]}
+                     "factor": nf * phases["factor"],
+                     "assemble_F": max(nx - nf, 0) * phases["assemble_F"],
+                     "solve": max(nx - nf, 0) * phases["solve"] + nf * max(phases["factor_solve"] - phases["factor"], 0.0)}
             dom = max(share, key=share.get)
             tr = traffic_tab.get(dom)
             traffic = tr["bytes_per_interval"] * n_local if tr else None

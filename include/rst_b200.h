@@ -125,6 +125,12 @@ int rst_b200_eval_jacobian(rst_b200_solver *s, int which_state);
 int rst_b200_factor(rst_b200_solver *s);
 /* dY = J^{-1} F (MatrixType::solve_sys on the cached factors) */
 int rst_b200_solve(rst_b200_solver *s);
+/* factor the current Jacobian blocks AND solve J dY = F with the residual the handle holds, in one call -- what the
+ * reference's solve_sys does every time (factor_from + solve_in_place, BVP_traits.rs:875-899).  Same result, bit for bit,
+ * as rst_b200_factor followed by rst_b200_solve; for 12-variable problems the right-hand side rides through the
+ * factorisation as a spare panel column (abd4.cuh), so the forward sweeps of that first solve are not run at all.
+ * The factors stay cached for later rst_b200_solve calls. */
+int rst_b200_factor_solve(rst_b200_solver *s);
 /* reductions of the current step against state `which_state` */
 int rst_b200_reduce(rst_b200_solver *s, int which_state, rst_b200_scalars *out);
 /* Y_trial = Y - lambda dY */

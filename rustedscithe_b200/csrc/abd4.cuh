@@ -50,6 +50,9 @@ struct Abd4Cfg {
     __host__ __device__ static constexpr int lt_off(int b) { return 4 * R2 * b - 8 * b * (b - 1); }
     static constexpr int LT = 4 * R2 * NB - 8 * NB * (NB - 1);
     static constexpr unsigned ALL = R2 == 32 ? 0xffffffffu : ((1u << R2) - 1u);
+    // nv = 12: the last column tile is half padding (columns 36..39).  Column NC can carry the right-hand side through the
+    // elimination for free (abd_factor4_kernel<.., RHS = true>): the factorisation then delivers what the forward sweep would.
+    static constexpr bool HAS_RHS_COL = (NC % 8) == 4;
 };
 
 __device__ __forceinline__ void dmma_m8n8k4(double2 &c, double a, double b) {
@@ -90,7 +93,8 @@ struct Abd4Tile {
 template <int NV, bool IDENT_B>
 struct Abd4Smem {
     using Cf = Abd4Cfg<NV>;
-    static constexpr int STG = (IDENT_B ? 1 : 2) * NV * NV;   // doubles staged per block row
+    static constexpr int STG_RHS = (IDENT_B ? 1 : 2) * NV * NV;   // where the staged right-hand side of the block row starts
+    static constexpr int STG = STG_RHS + (Cf::HAS_RHS_COL ? ((NV + 1) / 2) * 2 : 0);   // doubles staged per block row
     double pan[4 * Cf::R2];             // pivot-column panel [column plane][slot]; planes ordered 0, 2, 1, 3 (bank spread)
     double lb[4 * Cf::R2 + 8];          // -Lt of the block (A fragments): columns (0,1) of every slot, then (+8: other banks) columns (2,3)
     double pr[4 * 4];                   // pivot row of each of the block's 4 pivots (its own entry replaced by 1/pivot)
@@ -102,9 +106,13 @@ struct Abd4Smem {
 #ifndef ABD4_MIN_BLOCKS
 #define ABD4_MIN_BLOCKS 4
 #endif
-template <int NV, bool IDENT_B>
+// RHS = true (nv = 12 only): the right-hand side L.r rides along as panel column 3 nv, so that the factorisation also
+// produces the transformed right-hand side of the pivot rows (L.e) and of the condensed row (L.r_next) -- exactly what
+// abd_forward4_kernel computes from the stored Lt -- and the first linear solve after a refactorisation needs no forward sweep.
+template <int NV, bool IDENT_B, bool RHS = false>
 __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLevel L, unsigned *flags) {
     using Cf = Abd4Cfg<NV>;
+    static_assert(!RHS || Cf::HAS_RHS_COL, "the right-hand side column needs a half-padded last tile");
     using Pk = AbdPack<NV>;
     using Sm = Abd4Smem<NV, IDENT_B>;
     constexpr int R2 = Cf::R2, RT = Cf::RT, CT = Cf::CT, NB = Cf::NB, SH = Cf::SH, PITCH = Cf::PITCH, PITCH_W = Cf::PITCH_W;
@@ -129,6 +137,9 @@ __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLe
         if constexpr (!IDENT_B) {
             const char *srcB = reinterpret_cast<const char *>(L.B + g * (int64_t)BL);
             for (int c = lane; c < BL / 2; c += 32) cp_async16(dst + BL * 8 + c * 16, srcB + c * 16);
+        }
+        if constexpr (RHS) {
+            if (lane < NV / 2) cp_async16(dst + Sm::STG_RHS * 8 + lane * 16, reinterpret_cast<const char *>(L.r + g * NV) + lane * 16);
         }
         cp_async_commit();
     };
@@ -175,6 +186,9 @@ __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLe
                     if constexpr (IDENT_B) v = make_double2(idx == slot ? 1.0 : 0.0, idx + 1 == slot ? 1.0 : 0.0);
                     else v = *reinterpret_cast<const double2 *>(L.B + (g0 * NV + slot) * NV + idx);
                 }
+                if constexpr (RHS) {
+                    if (part == 3 && q == 2) v = make_double2(L.r[g0 * NV + slot], 0.0);
+                }
             }
             X[T][TC] = v;
         });
@@ -208,6 +222,9 @@ __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLe
                             else v = *reinterpret_cast<const double2 *>(stA + BL + t * NV + idx);
                         }
                     }
+                    if constexpr (RHS) {
+                        if (part == 3 && q == 2) v = make_double2(stA[Sm::STG_RHS + t], 0.0);
+                    }
                     X[T][TC] = v;
                 });
             } else {
@@ -222,7 +239,7 @@ __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLe
                         double2 lo_v = X[T][TC], hi_v = X[T][TC];
                         if constexpr (Tl::LO == 0) { if constexpr (TC + SH < CT) lo_v = X[T][TC + SH]; }
                         else if constexpr (Tl::LO != 1) lo_v = make_double2(0.0, 0.0);
-                        if constexpr (Tl::HI != 1) hi_v = make_double2(0.0, 0.0);
+                        if constexpr (Tl::HI != 1 && !(RHS && Tl::HI == 3)) hi_v = make_double2(0.0, 0.0);   // RHS: column 3 nv stays
                         X[T][TC] = hi ? hi_v : lo_v;
                     }
                 });
@@ -457,6 +474,9 @@ __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLe
             for (int TC = 0; TC < CT; ++TC) sts128_if(k >= 0, xs + k * PITCH_W + 8 * TC + 2 * q, X[T][TC]);
         }
         __syncwarp();
+        if constexpr (RHS) {                // transformed right-hand side of the pivot rows, in pivot order
+            if (lane < NV) L.e[g * NV + lane] = xs[lane * PITCH_W + Cf::NC];
+        }
         {   // coalesced write-out: lane handles doubles lane, lane + 32, ... of the record
             double *uef = L.UEF + g * (int64_t)Pk::UEF + lane;
             const char *xb = reinterpret_cast<const char *>(xs);
@@ -485,6 +505,9 @@ __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLe
                 const int idx = 8 * TC + 2 * q - part * NV;
                 if (part == 1) *reinterpret_cast<double2 *>(L.A_next + (slab * NV + t) * NV + idx) = X[T][TC];
                 if (part == 2) *reinterpret_cast<double2 *>(L.B_next + (slab * NV + t) * NV + idx) = X[T][TC];
+                if constexpr (RHS) {
+                    if (part == 3 && q == 2) L.r_next[slab * NV + t] = X[T][TC].x;
+                }
             });
         }
     }

@@ -136,6 +136,9 @@ struct SolverVT {
     // single-CTA tail of the level hierarchy (abd4.cuh); nullptr where the block size has no generation-4 kernels
     void (*tail_forward)(const AbdTail &, cudaStream_t);
     void (*tail_backward)(const AbdTail &, unsigned *flags, cudaStream_t);
+    // factorisation with the level's right-hand side riding along as a panel column (abd4.cuh, nv = 12): also writes L.e and
+    // L.r_next, i.e. what `forward` would compute from the stored factors, bit for bit; nullptr where there is no spare column
+    void (*factor_rhs)(const AbdLevel &, bool ident_b, unsigned *flags, cudaStream_t);
 };
 
 // kernel generation: "v1" = one panel row per lane + shuffle broadcast (abd.cuh); default "v3" (abd3.cuh).  Both write
@@ -190,6 +193,21 @@ struct SolverImpl {
         if (ident_b) abd_factor_kernel<NV, true><<<blocks, 128, 0, st>>>(L, flags);
         else abd_factor_kernel<NV, false><<<blocks, 128, 0, st>>>(L, flags);
     }
+    static constexpr bool HAS_RHS = []() { if constexpr (HAS_V4) return Abd4Cfg<NV>::HAS_RHS_COL; else return false; }();
+    static void factor_rhs(const AbdLevel &L, bool ident_b, unsigned *flags, cudaStream_t st) {
+        if constexpr (HAS_RHS) {
+            const unsigned blocks = (unsigned)((L.nslabs + 3) / 4);
+            if (ident_b) {
+                constexpr int smem = 4 * (int)sizeof(Abd4Smem<NV, true>);
+                cudaFuncSetAttribute(abd_factor4_kernel<NV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                abd_factor4_kernel<NV, true, true><<<blocks, 128, smem, st>>>(L, flags);
+            } else {
+                constexpr int smem = 4 * (int)sizeof(Abd4Smem<NV, false>);
+                cudaFuncSetAttribute(abd_factor4_kernel<NV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                abd_factor4_kernel<NV, false, true><<<blocks, 128, smem, st>>>(L, flags);
+            }
+        }
+    }
     static void forward(const AbdLevel &L, cudaStream_t st) {
         if constexpr (HAS_V4) {
             if (use_v4()) {
@@ -226,8 +244,9 @@ struct SolverImpl {
     }
     static SolverVT vt() {
         const bool tail = use_v4() && std::getenv("RST_B200_NO_TAIL") == nullptr;
+        const bool rhs = HAS_RHS && use_v4() && std::getenv("RST_B200_NO_RHS_COLUMN") == nullptr;
         return SolverVT{NV, &factor, &forward, &backward, &top, &residual, &reduce, &top_general,
-                        tail ? &tail_forward : nullptr, tail ? &tail_backward : nullptr};
+                        tail ? &tail_forward : nullptr, tail ? &tail_backward : nullptr, rhs ? &factor_rhs : nullptr};
     }
 };
 
@@ -388,6 +407,8 @@ struct rst_b200_solver {
     int64_t *d_stream_src = nullptr;
     double *d_stream_out = nullptr;
     bool have_jac = false, factored = false;
+    bool rhs_in_factors = false;   // the last factorisation carried F(y) along (SolverVT::factor_rhs): set by recalc_jacobian, consumed by the
+                                   // damped step that follows it in the same driver call (its first solve skips the local forward sweeps)
     int fuse_reduce_state = -1;        // >= 0: the next solve fuses the damping reductions for that state (nv = 2 path)
     int scal_slot = 0;                 // result slot (0/1) the next reduction writes to
     int reduce_ready_state = -1;
@@ -1155,7 +1176,11 @@ extern "C" int rst_b200_eval_jacobian(rst_b200_solver *s, int which_state) {
     return RST_B200_OK;
 }
 
-extern "C" int rst_b200_factor_local(rst_b200_solver *s) {
+static int factor_local_impl(rst_b200_solver *s, bool with_rhs);
+extern "C" int rst_b200_factor_local(rst_b200_solver *s) { return factor_local_impl(s, false); }
+
+// with_rhs: every level's factor kernel also eliminates the level's right-hand side (level 0: s->F) -- SolverVT::factor_rhs
+static int factor_local_impl(rst_b200_solver *s, bool with_rhs) {
     if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
     if (!s->have_jac) return fail(RST_B200_ERR_NOT_FACTORIZED, "no Jacobian has been evaluated");
     CUDA_TRY(cudaMemsetAsync(s->d_flags, 0, sizeof(unsigned), s->stream));
@@ -1174,7 +1199,8 @@ extern "C" int rst_b200_factor_local(rst_b200_solver *s) {
         return RST_B200_OK;
     }
     for (auto &lv : s->levels) {
-        s->sv.factor(lv.k, lv.ident_b, s->d_flags, s->stream);
+        if (with_rhs) s->sv.factor_rhs(lv.k, lv.ident_b, s->d_flags, s->stream);
+        else s->sv.factor(lv.k, lv.ident_b, s->d_flags, s->stream);
         s->launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -1340,8 +1366,12 @@ extern "C" int rst_b200_p2p_open(rst_b200_solver *s, const void *handles, size_t
     return RST_B200_OK;
 }
 
-extern "C" int rst_b200_factor(rst_b200_solver *s) {
-    TRY(rst_b200_factor_local(s));
+static int factor_impl(rst_b200_solver *s, bool with_rhs);
+extern "C" int rst_b200_factor(rst_b200_solver *s) { return factor_impl(s, false); }
+static bool can_factor_with_rhs(const rst_b200_solver *s) { return s->sv.factor_rhs != nullptr && !s->use_tps && !s->levels.empty(); }
+
+static int factor_impl(rst_b200_solver *s, bool with_rhs) {
+    TRY(factor_local_impl(s, with_rhs));
     if (fused_p2p(s)) {  // exchange + interface factorisation already ran inside the tail kernel
         s->factored = true;
         return RST_B200_OK;
@@ -1473,7 +1503,22 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
     return RST_B200_OK;
 }
 
-extern "C" int rst_b200_solve(rst_b200_solver *s) {
+static int solve_impl(rst_b200_solver *s, bool skip_local_forward);
+extern "C" int rst_b200_solve(rst_b200_solver *s) { return solve_impl(s, false); }
+
+extern "C" int rst_b200_factor_solve(rst_b200_solver *s) {
+    if (!s) return fail(RST_B200_ERR_INVALID, "null handle");
+    const bool with_rhs = can_factor_with_rhs(s);
+    TRY(factor_impl(s, with_rhs));
+    return solve_impl(s, with_rhs);
+}
+
+// skip_local_forward: the factorisation that just ran eliminated this right-hand side as well (factor_rhs): e and r_next of
+// every local level are already what the forward sweeps would write
+static int solve_impl(rst_b200_solver *s, bool skip_local_forward) {
+    if (skip_local_forward) {
+        if (!s || !s->factored) return fail(RST_B200_ERR_NOT_FACTORIZED, "solve before factor");
+    } else
     TRY(rst_b200_solve_local_forward(s));
     if (s->world > 1 && !fused_p2p(s)) {
         TRY(exchange(s, s->iface_rhs, s->gath_rhs, (int64_t)s->nv));
@@ -1594,10 +1639,11 @@ static int check_scalars(const rst_b200_scalars &sc) {
 }
 
 // NRBVP::step (:1782-1847) for state `which`: dY = J^{-1} F(y)
-static int newton_step(rst_b200_solver *s, int which) {   // enqueue-only; the caller counts the linear solve
-    TRY(rst_b200_eval_residual(s, which));
+// rhs_done: F(y) of this state was computed by the Jacobian pass and eliminated by the factorisation (rhs_in_factors)
+static int newton_step(rst_b200_solver *s, int which, bool rhs_done = false) {   // enqueue-only; the caller counts the linear solve
+    if (!rhs_done) TRY(rst_b200_eval_residual(s, which));
     s->fuse_reduce_state = which;  // the reduction that follows this solve refers to state `which`
-    TRY(rst_b200_solve(s));
+    TRY(solve_impl(s, rhs_done));
     s->fuse_reduce_state = -1;
     return RST_B200_OK;
 }
@@ -1650,11 +1696,12 @@ static int recalc_jacobian(rst_b200_solver *s, rst_b200_newton_stats *st) {
     const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;   // read per call: tests toggle it
     bool replayed = false;   // fixed launch sequence with fixed arguments per state buffer
     TRY(run_graphed(s, s->jac_graphs, (uintptr_t)s->Y, (s->world == 1 || s->p2p_enabled) && graphs_on, &replayed, [&]() -> int {
-        TRY(rst_b200_eval_jacobian(s, 0));
-        TRY(rst_b200_factor(s));
+        TRY(rst_b200_eval_jacobian(s, 0));        // F(y) and J(y) in one pass
+        TRY(factor_impl(s, can_factor_with_rhs(s)));
         return RST_B200_OK;
     }));
     if (replayed) s->have_jac = s->factored = true;
+    s->rhs_in_factors = can_factor_with_rhs(s);
     st->jac_recalcs++;
     st->factorizations++;
     return RST_B200_OK;
@@ -1681,16 +1728,18 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
     // on the device, so undamped step + first trial are enqueued back to back and the host synchronises ONCE.
     const bool speculative = (s->world == 1 || s->p2p_enabled) && o->max_damp_iter > 0;
     carry = carry && speculative;
+    const bool rhs_done = s->rhs_in_factors && !carry;   // first solve after recalc_jacobian: no residual pass, no forward sweeps
+    s->rhs_in_factors = false;
     s->scal_slot = 0;
     // The speculative sequence is ~25-45 launches with fixed arguments: small meshes are launch bound, so it is captured
     // into a CUDA graph (per Y / Y_trial parity) the second time it runs and replayed with one launch afterwards.
     const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;   // read per call: tests toggle it
     {
         bool replayed = false;
-        TRY(run_graphed(s, carry ? s->carry_graphs : s->step_graphs, (uintptr_t)s->Y, speculative && graphs_on, &replayed, [&]() -> int {
+        TRY(run_graphed(s, carry ? s->carry_graphs : s->step_graphs, (uintptr_t)s->Y | (rhs_done ? 1u : 0u), speculative && graphs_on, &replayed, [&]() -> int {
             const int64_t total = (s->n + 1) * (int64_t)s->nv;
             if (!carry) {
-                TRY(newton_step(s, 0));
+                TRY(newton_step(s, 0, rhs_done));
                 if (!speculative) return RST_B200_OK;
                 TRY(rst_b200_reduce_local(s, 0));
                 newton_trial_dev_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY, s->Yt, s->d_scal, total);

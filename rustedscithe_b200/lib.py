@@ -85,6 +85,7 @@ SYMBOLS = {
     "rst_b200_eval_jacobian": (C.c_int, [_H, C.c_int]),
     "rst_b200_factor": (C.c_int, [_H]),
     "rst_b200_solve": (C.c_int, [_H]),
+    "rst_b200_factor_solve": (C.c_int, [_H]),
     "rst_b200_reduce": (C.c_int, [_H, C.c_int, C.POINTER(Scalars)]),
     "rst_b200_make_trial": (C.c_int, [_H, C.c_double]),
     "rst_b200_accept_trial": (C.c_int, [_H]),

@@ -350,6 +350,10 @@ class NRBVP:
     def solve(self):
         self._ck(self.L.rst_b200_solve(self.handle))
 
+    def factor_solve(self):
+        """factor_from + solve_in_place in one call (the reference's solve_sys, BVP_traits.rs:875-899); factors stay cached."""
+        self._ck(self.L.rst_b200_factor_solve(self.handle))
+
     def reduce(self, which=0):
         sc = _lib.Scalars()
         self._ck(self.L.rst_b200_reduce(self.handle, which, C.byref(sc)))

@@ -611,8 +611,8 @@ def test_carried_undamped_step_is_bit_identical_to_recomputing_it(tmp_path):
     import subprocess
     import sys
     res = {}
-    for tag, env_extra in (("carry", {}), ("recompute", {"RST_B200_NO_CARRY": "1"})):
-        env = {k: v for k, v in os.environ.items() if k != "RST_B200_NO_CARRY"}
+    for tag, env_extra in (("carry", {}), ("recompute", {"RST_B200_NO_CARRY": "1"}), ("no_rhs_column", {"RST_B200_NO_RHS_COLUMN": "1"})):
+        env = {k: v for k, v in os.environ.items() if k not in ("RST_B200_NO_CARRY", "RST_B200_NO_RHS_COLUMN")}
         env.update(env_extra)
         path = tmp_path / f"{tag}.json"
         subprocess.run([sys.executable, "-c", _CARRY_SCRIPT, str(path)], check=True, env=env,
@@ -624,3 +624,42 @@ def test_carried_undamped_step_is_bit_identical_to_recomputing_it(tmp_path):
         assert (a["it"], a["ls"], a["jac"]) == (b["it"], b["ls"], b["jac"]), key
         assert b["reused"] == 0
     assert res["carry"]["flame12"]["reused"] >= 1
+    # nv = 12: the right-hand side eliminated inside the factorisation (abd_factor4_kernel<.., RHS>) against the forward sweeps
+    for key in res["carry"]:
+        a, b = res["carry"][key], res["no_rhs_column"][key]
+        assert (a["it"], a["ls"], a["jac"]) == (b["it"], b["ls"], b["jac"]), key
+        ya = np.frombuffer(bytes.fromhex(a["sol"]), dtype=np.float64)
+        yb = np.frombuffer(bytes.fromhex(b["sol"]), dtype=np.float64)
+        assert np.max(np.abs(ya - yb) / np.maximum(np.abs(yb), 1.0)) < 1e-13, key
+        print(f"rhs column vs forward sweeps, {key}: bit-identical = {a['sol'] == b['sol']}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key,n", [("flame12", 5000), ("flame12", 37), ("combustion6", 3000), ("linear2", 4000), ("coupled64", 200)])
+def test_factor_solve_equals_factor_then_solve(key, n):
+    """rst_b200_factor_solve (the reference's solve_sys: factor_from + solve_in_place in one call; nv = 12 carries the right-hand
+    side through the factorisation instead of running the forward sweeps) against rst_b200_factor + rst_b200_solve: same bits,
+    and the cached factors serve a later plain solve."""
+    spec = problems.get(key)
+    sv = NRBVP(key, spec.guess(n), n, DampedSolverOptions.from_spec(spec))
+    import ctypes as C
+    from rustedscithe_b200 import lib as rlib
+    m = (n + 1) * spec.nv
+
+    def dY():
+        out = np.empty(m)
+        rlib.check(sv.L.rst_b200_memcpy(C.c_void_p(out.ctypes.data), C.c_void_p(sv.device_ptr(4)), m * 8, 2))
+        return out
+
+    sv.eval_jacobian(0)
+    sv.factor()
+    sv.solve()
+    want = dY()
+    sv.eval_jacobian(0)
+    sv.factor_solve()
+    got = dY()
+    np.testing.assert_array_equal(got, want)
+    sv.solve()                       # plain solve (forward sweeps and all) on the factors factor_solve left behind, same F
+    np.testing.assert_array_equal(dY(), want)
+    assert np.all(np.isfinite(want)) and np.abs(want).max() > 0
+    sv.close()

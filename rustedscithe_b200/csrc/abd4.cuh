@@ -138,9 +138,11 @@ __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLe
             const char *srcB = reinterpret_cast<const char *>(L.B + g * (int64_t)BL);
             for (int c = lane; c < BL / 2; c += 32) cp_async16(dst + BL * 8 + c * 16, srcB + c * 16);
         }
+#ifndef ABD4_X_NORSTAGE
         if constexpr (RHS) {
             if (lane < NV / 2) cp_async16(dst + Sm::STG_RHS * 8 + lane * 16, reinterpret_cast<const char *>(L.r + g * NV) + lane * 16);
         }
+#endif
         cp_async_commit();
     };
     if (len > 1) stage(g0 + 1, 1);
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLe
         // ---- blocked elimination of the nv columns of M ------------------------------------------------------
         unsigned cand_mask = Cf::ALL;       // slots not pivoted yet in this block row
         int pv = -1;                        // row layout (lane = slot): pivot index of my slot
-        unsigned pword[NB];                 // pivot slots, 4 per word
+        unsigned mypword = 0u;              // lane b: the pivot slots of block b, 4 per word
         double *lt_g = L.Lm + g * (int64_t)Cf::LT;
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLe
                 if (is_piv) { mypiv = ii; pv = 4 * b + ii; cand = false; }
                 cand_mask &= ~(1u << p);
             }
-            pword[b] = (unsigned)ps[0] | ((unsigned)ps[1] << 8) | ((unsigned)ps[2] << 16) | ((unsigned)ps[3] << 24);
+            if (lane == b) mypword = (unsigned)ps[0] | ((unsigned)ps[1] << 8) | ((unsigned)ps[2] << 16) | ((unsigned)ps[3] << 24);
             // warp-uniform values, one per lane: lanes 0..5  n_k = num[k] / piv[j(k)]  (j = 0 0 1 0 1 2), lanes 6..9  1 / piv[lane - 6]
             double n10, n20, n21, n30, n31, n32, rinv[4];
             {
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLe
                 if (is_piv) { mypiv = ii; pv = 4 * b + ii; cand = false; }
                 cand_mask &= ~(1u << p);
             }
-            pword[b] = (unsigned)ps[0] | ((unsigned)ps[1] << 8) | ((unsigned)ps[2] << 16) | ((unsigned)ps[3] << 24);
+            if (lane == b) mypword = (unsigned)ps[0] | ((unsigned)ps[1] << 8) | ((unsigned)ps[2] << 16) | ((unsigned)ps[3] << 24);
             // multipliers of my slot: candidates keep all four, pivot ii keeps those of the earlier pivots, others none
             const int lim = cand_at_start ? mypiv : 0;
             const double l0 = lim > 0 ? a[0] : 0.0, l1 = lim > 1 ? a[1] : 0.0, l2 = lim > 2 ? a[2] : 0.0, l3 = lim > 3 ? a[3] : 0.0;
@@ -461,10 +463,7 @@ __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLe
         }
         // ---- pivot rows -> U | E | F (layout of abd.cuh), pivot slots -> piv --------------------------------------
         if (lane < NB) {
-            unsigned w = pword[0];
-#pragma unroll
-            for (int b = 1; b < NB; ++b) w = (lane == b) ? pword[b] : w;
-            reinterpret_cast<unsigned *>(L.piv + g * (int64_t)Cf::PIV_STRIDE)[lane] = w;
+            reinterpret_cast<unsigned *>(L.piv + g * (int64_t)Cf::PIV_STRIDE)[lane] = mypword;
         }
 #ifndef ABD4_X_NOWRITE
 #pragma unroll
@@ -474,9 +473,11 @@ __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLe
             for (int TC = 0; TC < CT; ++TC) sts128_if(k >= 0, xs + k * PITCH_W + 8 * TC + 2 * q, X[T][TC]);
         }
         __syncwarp();
+#ifndef ABD4_X_NOESTORE
         if constexpr (RHS) {                // transformed right-hand side of the pivot rows, in pivot order
             if (lane < NV) L.e[g * NV + lane] = xs[lane * PITCH_W + Cf::NC];
         }
+#endif
         {   // coalesced write-out: lane handles doubles lane, lane + 32, ... of the record
             double *uef = L.UEF + g * (int64_t)Pk::UEF + lane;
             const char *xb = reinterpret_cast<const char *>(xs);

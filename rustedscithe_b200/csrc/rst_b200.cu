@@ -369,6 +369,7 @@ struct rst_b200_solver {
     // device buffers
     double *Y = nullptr, *Yt = nullptr, *F = nullptr, *A = nullptr, *B = nullptr, *dY = nullptr;
     double *d_mesh = nullptr, *d_params = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_rtol = nullptr;
+    double *Y_home = nullptr; // the buffer Y starts in: the Newton drivers begin every solve there (stable CUDA-graph keys)
     double *dY1 = nullptr;    // step of a damping trial (the undamped step in dY must survive rejected trials)
     double *sol = nullptr;    // buffer the linear solve currently writes to (dY or dY1)
     double *Ysave = nullptr;  // device-side checkpoint of Y (rst_b200_checkpoint)
@@ -630,6 +631,7 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
         const int64_t n = s->n;
         const size_t nodes = (size_t)(n + 1) * nv;
         TRY(dev_alloc(s, &s->Y, nodes));
+        s->Y_home = s->Y;
         TRY(dev_alloc(s, &s->Yt, nodes));
         TRY(dev_alloc(s, &s->dY, nodes));
         TRY(dev_alloc(s, &s->dY1, nodes));
@@ -1842,6 +1844,13 @@ extern "C" int rst_b200_newton_solve(rst_b200_solver *s, const rst_b200_newton_o
     CUDA_TRY(cudaSetDevice(s->device));
     std::memset(st, 0, sizeof(*st));
     const auto t_begin = std::chrono::steady_clock::now();
+    // Y and Y_trial swap roles with every accepted iteration, and the CUDA-graph caches are keyed by the buffer Y lives in: after
+    // a solve with an odd number of iterations the next one would meet every key in its other flavour (and pay the captures a
+    // second time).  Start every solve from the home buffer: one device-to-device copy of the state when the roles are swapped.
+    if (s->Y != s->Y_home && s->Yt == s->Y_home) {
+        CUDA_TRY(cudaMemcpyAsync(s->Y_home, s->Y, (size_t)(s->n + 1) * s->nv * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        std::swap(s->Y, s->Yt);
+    }
     bool have_jac = false, recalc = true;
     // carry: the accepted first trial of the previous iteration IS this iteration's undamped step (same y, same factors)
     static const bool carry_on = std::getenv("RST_B200_NO_CARRY") == nullptr;

@@ -3,7 +3,7 @@
 Each list is `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none`
 over `bench.py --workload <w> --steps K --warmup 3 --no-cpu --no-secondary`.  For every phase bench.py times
 (assemble_FJ, assemble_F, factor, solve) the DRAM bytes of ALL its kernels are summed and divided by the number of times the
-phase ran (= launches of its level-0 kernel) and by the mesh size: bytes per interval, the figure `roofline.traffic` scales.
+phase ran and by the mesh size: bytes per interval, the figure `roofline.traffic` scales.
 """
 import collections
 import csv
@@ -35,7 +35,11 @@ def main():
         rows = list(csv.reader(open(os.path.join(ROOT, path))))
         hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
         idx = {h: i for i, h in enumerate(rows[hi])}
-        per = collections.defaultdict(lambda: collections.defaultdict(float))    # phase -> (kernel, grid) -> bytes / launches
+        # phase -> (kernel, grid) -> [bytes, launches].  A phase execution launches every (kernel, grid) of the phase once (one
+        # launch per level and sweep direction), so its traffic is the sum over them of the mean bytes per launch -- robust
+        # against phases that skip kernels (the first solve after a refactorisation runs no forward sweeps).  The two variants of
+        # the nv = 12 factor kernel (with / without the right-hand-side column) count as one kernel.
+        per = collections.defaultdict(lambda: collections.defaultdict(lambda: [0.0, 0]))
         for r in rows[hi + 1:]:
             if len(r) < len(rows[hi]):
                 continue
@@ -44,21 +48,19 @@ def main():
             if ph is None:
                 continue
             v = float(r[idx["Metric Value"]].replace(",", ""))
-            k = (name.split("(")[0], grid)
+            kname = re.sub(r"(abd_factor4_kernel<\d+, \d), \d>", r"\1>", name.split("(")[0])
+            kname = kname.replace("tps_backward_reduce_kernel", "tps_backward_kernel")   # level-0 sweep with / without the fused reductions
+            k = (kname, grid)
             if metric.startswith("dram__bytes"):
-                per[ph][k] += v
-                per[ph][("bytes", "total")] += v
+                per[ph][k][0] += v
             elif metric.startswith("gpu__time"):
-                per[ph][(k, "launches")] += 1
+                per[ph][k][1] += 1
         out[key] = {}
         for ph, d in per.items():
-            launches = {k[0]: v for k, v in d.items() if isinstance(k[0], tuple)}
-            # the phase ran as often as its biggest-grid kernel was launched
-            big = max(launches, key=lambda kg: int(kg[1].strip("()").split(",")[0]))
-            runs = launches[big]
-            out[key][ph] = {"bytes_per_interval": d[("bytes", "total")] / runs / n, "phase_runs_in_capture": int(runs),
-                            "source": f"{path}: dram__bytes_read.sum + dram__bytes_write.sum of every kernel of the phase, "
-                                      f"per phase execution, / {n} intervals"}
+            total = sum(b / max(c, 1) for b, c in d.values())
+            out[key][ph] = {"bytes_per_interval": total / n, "kernels_per_phase_execution": len(d),
+                            "source": f"{path}: dram__bytes_read.sum + dram__bytes_write.sum, mean per launch of every (kernel, grid) "
+                                      f"of the phase, summed, / {n} intervals"}
     json.dump(out, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
     for key, d in out.items():
         print(key, {ph: round(v["bytes_per_interval"], 1) for ph, v in d.items()})

@@ -377,7 +377,9 @@ __global__ void __launch_bounds__(128, ABD4_MIN_BLOCKS) abd_factor4_kernel(AbdLe
                 // by 31 - lane): ties and values equal in their leading 15 mantissa bits resolve to the lowest slot
                 const unsigned hw = (unsigned)__double2hiint(a[ii]) & 0x7fffffffu;
                 const unsigned key = cand ? (((hw & ~31u) | (unsigned)(31 - lane)) + 1u) : 0u;
-                const double myr = fast_rcp(a[ii]);        // every lane inverts its own entry while the REDUX is in flight
+                // (the compiler predicates the Newton steps on the pivot lane and issues them after the REDUX; forcing them ahead
+                // of it with a volatile block measures the same: this kernel is throughput bound, not chain bound)
+                const double myr = fast_rcp(a[ii]);
                 const unsigned mx = __reduce_max_sync(RST_FULL_MASK, key);
                 const int p = 31 - (int)((mx - 1u) & 31u);
                 ps[ii] = p;

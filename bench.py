@@ -479,7 +479,8 @@ def run_workload(args, workload, rank, world, local_rank, primary):
                     sv.p2p_open(handles)
                 dist.barrier()
             guess = pipe.pinned(y0)
-            sols, _ = pipe.solve_many([guess, guess])              # untimed: warm-up and check against the one-handle answer
+            # untimed: three solves per lane (direct launches, CUDA-graph capture, replay) and the check against the one-handle answer
+            sols, _ = pipe.solve_many([guess] * 6)
             if not all(s_ is not None and np.array_equal(s_, out_np) for s_ in sols):
                 raise SystemExit("pipelined e2e: the lanes did not reproduce the one-handle solution")
             del sols

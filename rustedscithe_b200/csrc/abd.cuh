@@ -351,9 +351,31 @@ __device__ __forceinline__ void abd_backward_warp(const AbdLevel &L, int64_t war
     }
 }
 
+// Programmatic dependent launch (the host launches the sweeps with cudaLaunchAttributeProgrammaticStreamSerialization):
+// a sweep kernel lets its successor be scheduled at once, pulls the first factors it will need into L2 -- they are static,
+// nothing a predecessor writes -- and only then waits for the predecessor's results.  Without the launch attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int NV>
 __global__ void __launch_bounds__(128) abd_backward_kernel(AbdLevel L) {
-    abd_backward_warp<NV>(L, (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), threadIdx.x & 31);
+    const int64_t warp_index = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    {   // U | E | F of the last block row of this lane group's slab
+        constexpr int G = next_pow2(NV);
+        const int64_t slab = warp_index * (32 / G) + lane / G;
+        if (slab < L.nslabs) {
+            const int64_t g0 = slab * (int64_t)L.S;
+            const int64_t last = g0 + ((L.n - g0) < (int64_t)L.S ? (L.n - g0) : (int64_t)L.S) - 1;
+            const char *p = reinterpret_cast<const char *>(L.UEF + last * (int64_t)AbdPack<NV>::UEF);
+            for (int off = (lane & (G - 1)) * 128; off < AbdPack<NV>::UEF * 8; off += G * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+        }
+    }
+    pdl_wait();
+    abd_backward_warp<NV>(L, warp_index, lane);
 }
 
 // ------------------------------------------------------------------------------------------------

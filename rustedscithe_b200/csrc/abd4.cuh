@@ -593,7 +593,17 @@ __device__ __forceinline__ void abd_forward4_slab(const AbdLevel &L, int64_t sla
 
 template <int NV>
 __global__ void __launch_bounds__(128) abd_forward4_kernel(AbdLevel L) {
-    abd_forward4_slab<NV>(L, (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), threadIdx.x & 31);
+    const int64_t slab = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();   // programmatic dependent launch, see abd.cuh
+    if (slab < L.nslabs && slab * (int64_t)L.S + 1 < L.n) {   // Lt and pivot record of the slab's first elimination step
+        const int64_t g1 = slab * (int64_t)L.S + 1;
+        if (lane * 128 < Abd4Cfg<NV>::LT * 8)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(L.Lm + g1 * (int64_t)Abd4Cfg<NV>::LT) + lane * 128));
+        if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(L.piv + g1 * (int64_t)Abd4Cfg<NV>::PIV_STRIDE));
+    }
+    pdl_wait();
+    abd_forward4_slab<NV>(L, slab, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -627,10 +637,12 @@ __device__ __forceinline__ void prefetch_l2_range(const void *p, size_t bytes) {
 template <int NV>
 __global__ void __launch_bounds__(ABD_TAIL_THREADS) abd_tail_forward_kernel(AbdTail T) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    pdl_launch_dependents();
     for (int l = 0; l < T.nlev; ++l) {
         prefetch_l2_range(T.lv[l].Lm, (size_t)T.lv[l].n * Abd4Cfg<NV>::LT * sizeof(double));
         prefetch_l2_range(T.lv[l].piv, (size_t)T.lv[l].n * Abd4Cfg<NV>::PIV_STRIDE);
     }
+    pdl_wait();                // the factors travel while the predecessor finishes (programmatic dependent launch, abd.cuh)
     for (int l = 0; l < T.nlev; ++l) {
         const AbdLevel &L = T.lv[l];
         for (int64_t slab = warp; slab < L.nslabs; slab += nwarps) abd_forward4_slab<NV>(L, slab, lane);
@@ -643,10 +655,10 @@ __global__ void __launch_bounds__(ABD_TAIL_THREADS) abd_tail_backward_kernel(Abd
     __shared__ AbdTopSmem<NV> top_sm;
     constexpr int GPW = 32 / next_pow2(NV);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int l = T.nlev - 1; l >= 0; --l) {
-        prefetch_l2_range(T.lv[l].UEF, (size_t)T.lv[l].n * AbdPack<NV>::UEF * sizeof(double));
-        prefetch_l2_range(T.lv[l].e, (size_t)T.lv[l].n * NV * sizeof(double));
-    }
+    pdl_launch_dependents();
+    for (int l = T.nlev - 1; l >= 0; --l) prefetch_l2_range(T.lv[l].UEF, (size_t)T.lv[l].n * AbdPack<NV>::UEF * sizeof(double));
+    pdl_wait();
+    for (int l = T.nlev - 1; l >= 0; --l) prefetch_l2_range(T.lv[l].e, (size_t)T.lv[l].n * NV * sizeof(double));
     if (T.do_top) {
         if (warp == 0) abd_top_solve_warp<NV>(top_sm, T.C, T.D, T.g, T.Ztop, T.left_mask, T.right_mask, flags, lane);
         __syncthreads();

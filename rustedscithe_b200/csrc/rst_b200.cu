@@ -153,6 +153,24 @@ static int kernel_generation() {
     return gen;
 }
 
+// Launch with programmatic stream serialisation: the kernel may be scheduled while its predecessor in the stream is still
+// running; it orders itself with griddepcontrol.wait (pdl_wait, abd.cuh).  Captured into CUDA graphs as a programmatic edge.
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+    static const bool on = std::getenv("RST_B200_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = on ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int NV>
 struct SolverImpl {
     static unsigned grid_for(int64_t nslabs, int lanes) {
@@ -211,14 +229,14 @@ struct SolverImpl {
     static void forward(const AbdLevel &L, cudaStream_t st) {
         if constexpr (HAS_V4) {
             if (use_v4()) {
-                abd_forward4_kernel<NV><<<(unsigned)((L.nslabs + 3) / 4), 128, 0, st>>>(L);
+                launch_pdl(abd_forward4_kernel<NV>, (unsigned)((L.nslabs + 3) / 4), 128u, st, L);
                 return;
             }
         }
         abd_forward_kernel<NV><<<grid_for(L.nslabs, 2 * NV), 128, 0, st>>>(L);
     }
     static void backward(const AbdLevel &L, cudaStream_t st) {
-        abd_backward_kernel<NV><<<grid_for(L.nslabs, NV), 128, 0, st>>>(L);
+        launch_pdl(abd_backward_kernel<NV>, grid_for(L.nslabs, NV), 128u, st, L);
     }
     static void top(const double *C, const double *D, const double *g, double *Z, unsigned long long lm,
                     unsigned long long rm, unsigned *flags, int, cudaStream_t st) {
@@ -237,10 +255,10 @@ struct SolverImpl {
         abd_top_general_kernel<NV><<<1, 32, 0, st>>>(C, D, g, Ba, ba, na, Bb, bb, nb, Z, flags);
     }
     static void tail_forward(const AbdTail &T, cudaStream_t st) {
-        if constexpr (HAS_V4) abd_tail_forward_kernel<NV><<<1, ABD_TAIL_THREADS, 0, st>>>(T);
+        if constexpr (HAS_V4) launch_pdl(abd_tail_forward_kernel<NV>, 1u, (unsigned)ABD_TAIL_THREADS, st, T);
     }
     static void tail_backward(const AbdTail &T, unsigned *flags, cudaStream_t st) {
-        if constexpr (HAS_V4) abd_tail_backward_kernel<NV><<<1, ABD_TAIL_THREADS, 0, st>>>(T, flags);
+        if constexpr (HAS_V4) launch_pdl(abd_tail_backward_kernel<NV>, 1u, (unsigned)ABD_TAIL_THREADS, st, T, flags);
     }
     static SolverVT vt() {
         const bool tail = use_v4() && std::getenv("RST_B200_NO_TAIL") == nullptr;

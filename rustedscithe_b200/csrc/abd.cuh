@@ -351,13 +351,6 @@ __device__ __forceinline__ void abd_backward_warp(const AbdLevel &L, int64_t war
     }
 }
 
-// Programmatic dependent launch (the host launches the sweeps with cudaLaunchAttributeProgrammaticStreamSerialization):
-// a sweep kernel lets its successor be scheduled at once, pulls the first factors it will need into L2 -- they are static,
-// nothing a predecessor writes -- and only then waits for the predecessor's results.  Without the launch attribute both
-// instructions are no-ops.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 template <int NV>
 __global__ void __launch_bounds__(128) abd_backward_kernel(AbdLevel L) {
     const int64_t warp_index = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

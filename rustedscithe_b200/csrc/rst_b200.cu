@@ -1407,11 +1407,11 @@ extern "C" int rst_b200_solve_local_forward(rst_b200_solver *s) {
     if (!s->factored) return fail(RST_B200_ERR_NOT_FACTORIZED, "solve before factor");
     if (s->use_tps) {
         for (auto &lv : s->tps_big) {
-            tps_forward_kernel<2, TPS_S><<<(unsigned)((lv.nslabs + tps_block() - 1) / tps_block()), tps_block(), 0, s->stream>>>(lv);
+            launch_pdl(tps_forward_kernel<2, TPS_S>, (unsigned)((lv.nslabs + tps_block() - 1) / tps_block()), (unsigned)tps_block(), s->stream, lv);
             s->launches++;
         }
         if (s->world > 1 && !fused_p2p(s)) {  // otherwise the tail's forward sweep is fused with closure + backward sweep
-            tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, iface_args(s, false), 0ull, 1, s->d_flags);
+            launch_pdl(tps_tail_solve_kernel<2, TPS_S>, 1u, 256u, s->stream, s->tps_tail, iface_args(s, false), 0ull, 1, s->d_flags);
             s->launches++;
         }
         CUDA_TRY(cudaGetLastError());
@@ -1435,8 +1435,8 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
     if (s->use_tps && (s->world == 1 || fused_p2p(s))) {
         const bool fused = fused_p2p(s);
         // forward sweeps -> closure (1 GPU) or NVLink interface exchange + solve (multi GPU) -> backward sweeps: ONE launch
-        tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, iface_args(s, fused), 0ull /* sequence number lives on the device (P2pPeers::seq_dev) */,
-                                                                   fused ? 13 : 7, s->d_flags);
+        launch_pdl(tps_tail_solve_kernel<2, TPS_S>, 1u, 256u, s->stream, s->tps_tail, iface_args(s, fused), 0ull /* sequence number lives on the device (P2pPeers::seq_dev) */,
+                   fused ? 13 : 7, s->d_flags);
         s->launches++;
         for (int i = (int)s->tps_big.size() - 1; i >= 0; --i) {
             const TpsLevel &lv = s->tps_big[i];
@@ -1450,11 +1450,11 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
                 R.has_left = (s->rank == 0); R.has_right = (s->rank == s->world - 1);
                 R.n_own = (s->rank == s->world - 1) ? s->n + 1 : s->n;
                 R.partials = s->d_partials;
-                tps_backward_reduce_kernel<2, TPS_S><<<blocks, tb, 0, s->stream>>>(lv, R);
+                launch_pdl(tps_backward_reduce_kernel<2, TPS_S>, blocks, (unsigned)tb, s->stream, lv, R);
                 s->reduce_ready = (int)blocks;
                 s->reduce_ready_state = s->fuse_reduce_state;
             } else {
-                tps_backward_kernel<2, TPS_S><<<blocks, tb, 0, s->stream>>>(lv);
+                launch_pdl(tps_backward_kernel<2, TPS_S>, blocks, (unsigned)tb, s->stream, lv);
             }
             s->launches++;
         }
@@ -1481,7 +1481,7 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
         s->launches++;
     }
     if (s->use_tps) {
-        tps_tail_solve_kernel<2, TPS_S><<<1, 256, 0, s->stream>>>(s->tps_tail, iface_args(s, false), 0ull, 4, s->d_flags);
+        launch_pdl(tps_tail_solve_kernel<2, TPS_S>, 1u, 256u, s->stream, s->tps_tail, iface_args(s, false), 0ull, 4, s->d_flags);
         s->launches++;
         for (int i = (int)s->tps_big.size() - 1; i >= 0; --i) {
             const TpsLevel &lv = s->tps_big[i];
@@ -1495,11 +1495,11 @@ extern "C" int rst_b200_solve_reduced_backward(rst_b200_solver *s) {
                 R.has_left = (s->rank == 0); R.has_right = (s->rank == s->world - 1);
                 R.n_own = (s->rank == s->world - 1) ? s->n + 1 : s->n;
                 R.partials = s->d_partials;
-                tps_backward_reduce_kernel<2, TPS_S><<<blocks, tb, 0, s->stream>>>(lv, R);
+                launch_pdl(tps_backward_reduce_kernel<2, TPS_S>, blocks, (unsigned)tb, s->stream, lv, R);
                 s->reduce_ready = (int)blocks;
                 s->reduce_ready_state = s->fuse_reduce_state;
             } else {
-                tps_backward_kernel<2, TPS_S><<<blocks, tb, 0, s->stream>>>(lv);
+                launch_pdl(tps_backward_kernel<2, TPS_S>, blocks, (unsigned)tb, s->stream, lv);
             }
             s->launches++;
         }

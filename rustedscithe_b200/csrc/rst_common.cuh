@@ -38,4 +38,12 @@ __device__ __forceinline__ void st_cs2(double2 *p, double2 v) { __stcs(p, v); }
 __device__ __forceinline__ double ld_cs(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ double2 ld_cs2(const double2 *p) { return __ldcs(p); }
 
+// Programmatic dependent launch (the host launches the sweeps with cudaLaunchAttributeProgrammaticStreamSerialization):
+// a sweep kernel lets its successor be scheduled at once, pulls the first factors it will need into L2 -- they are static,
+// nothing a predecessor writes -- and only then waits for the predecessor's results.  Without the launch attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+
 }  // namespace rst

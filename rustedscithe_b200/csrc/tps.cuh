@@ -367,11 +367,15 @@ __global__ void __launch_bounds__(128) tps_factor_kernel(TpsLevel L, unsigned *f
 }
 template <int NV, int S>
 __global__ void __launch_bounds__(128) tps_forward_kernel(TpsLevel L) {
+    pdl_launch_dependents();   // programmatic dependent launch (rst_common.cuh): scheduled under the predecessor's tail
+    pdl_wait();
     const int64_t slab = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slab < L.nslabs) tps_forward_slab<NV, S>(L, slab);
 }
 template <int NV, int S>
 __global__ void __launch_bounds__(128) tps_backward_kernel(TpsLevel L) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t slab = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slab < L.nslabs) tps_backward_slab<NV, S>(L, slab);
 }
@@ -379,6 +383,8 @@ __global__ void __launch_bounds__(128) tps_backward_kernel(TpsLevel L) {
 // level-0 backward sweep with the damping reductions fused in; one partial result per block
 template <int NV, int S>
 __global__ void __launch_bounds__(128) tps_backward_reduce_kernel(TpsLevel L, TpsReduce R) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t slab = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     TpsRedAcc acc{0.0, 0.0, 1.0, 0.0};
     if (slab < L.nslabs) {
@@ -470,6 +476,7 @@ __device__ void tps_top_solve(const double *C, const double *D, const double *g,
 template <int NV, int S>
 __global__ void __launch_bounds__(256) tps_tail_solve_kernel(TpsTail T, P2pIface I, unsigned long long seq, int phases,
                                                              unsigned *flags) {
+    pdl_launch_dependents();
     // The tail runs right after the level-0..2 sweeps have streamed > 100 MB through the L2: its own factors (a few
     // hundred KB) are gone by then and every slab step would pay a dependent DRAM round trip.  Pull them back in one burst.
     if (phases & 5) {
@@ -485,6 +492,7 @@ __global__ void __launch_bounds__(256) tps_tail_solve_kernel(TpsTail T, P2pIface
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + off));
         }
     }
+    pdl_wait();                // the factors travel while the predecessor finishes
     if (phases & 1) {
         for (int l = 0; l < T.nlevels; ++l) {
             const TpsLevel &L = T.lv[l];

@@ -1560,7 +1560,11 @@ extern "C" int rst_b200_reduce_local(rst_b200_solver *s, int which_state) {
     ReduceArgs a{};
     a.Y = which_state ? s->Yt : s->Y;
     a.dY = s->sol;
-    a.F = s->F;
+    // NRBVP::step scans F and the step for NaN (NR_Damp_solver_damped.rs:1821-1826, :1839-1844).  Every entry of F is the
+    // right-hand side of exactly one pivot row on some level and enters that row's solution component additively, and NaN
+    // survives every arithmetic operation (also NaN * 0): a NaN in F is a NaN in the step, which the scan of the step reports
+    // with the same status.  Reading F again (8 nv bytes per interval and solve) would add nothing.
+    a.F = nullptr;
     a.lo = s->d_lo; a.hi = s->d_hi; a.rtol = s->d_rtol;
     // ranks own nodes [0, n) of their slab; the last rank also owns global node N
     a.n_nodes = (s->rank == s->world - 1) ? s->n + 1 : s->n;

@@ -512,7 +512,14 @@ static int default_slab(int64_t n, int requested) {
     }
     // measured at nv = 12, 1e6 rows (solve ms): S = 8 1.090, 12 1.065, 16 1.049, 32 1.078, 64 1.107 -- longer slabs mean fewer
     // levels but a longer dependent chain per warp; nv = 64: 16 beats 32 as well
-    if (n >= (1 << 12)) return 16;
+    if (n >= (1 << 12)) {
+        if (n < (1 << 17))
+            if (const char *e = std::getenv("RST_B200_SLAB_MID")) {   // experiment: slab length of the levels with 4096 <= n < 131072 rows
+                const int v = std::atoi(e);
+                if (v >= 2) return v;
+            }
+        return 16;
+    }
     // small levels are latency bound (one dependent chain of S - 1 eliminations per slab): short slabs, more levels --
     // the levels below ABD_TAIL_ROWS rows share one launch per sweep (abd4.cuh), so extra levels are nearly free
     return 4;

@@ -1743,13 +1743,15 @@ static void unpack_scalars(const double *h, rst_b200_scalars *sc) {
     sc->sumsq_step = h[0]; sc->tol_sum = h[1]; sc->fbound = h[2]; sc->nan_flag = h[3]; sc->device_flags = h[4];
 }
 
-// `carry` (in): the previous iteration accepted its FIRST (speculative) trial and the factors are unchanged, so this
-// iteration's undamped step and its scalars are the trial's (newton_trial_carry_kernel) and are not recomputed.
-// `*first_trial_accepted` (out): this iteration ended that way.
-static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b200_newton_stats *st, int *status, bool carry = false,
-                       bool *first_trial_accepted = nullptr) {
+// `carry_slot` (in, >= 0): the previous iteration accepted a trial and the factors are unchanged, so this iteration's undamped
+// step and its scalars are that trial's (newton_trial_carry_kernel) and are not recomputed; the value says which device
+// scalar slot holds them (1: speculative first trial, 0: a later trial of the damping loop).
+// `*accepted_slot` (out): the same for the trial this iteration accepted, -1 if it cannot be carried.
+static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b200_newton_stats *st, int *status, int carry_slot = -1,
+                       int *accepted_slot = nullptr) {
     rst_b200_scalars sc{}, sc1{};
-    if (first_trial_accepted) *first_trial_accepted = false;
+    if (accepted_slot) *accepted_slot = -1;
+    bool carry = carry_slot >= 0;
     // trial steps go to dY1: the undamped step in dY is re-used by every damping trial (:1934, :1971)
     struct Restore {
         rst_b200_solver *s;
@@ -1767,7 +1769,7 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
     const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;   // read per call: tests toggle it
     {
         bool replayed = false;
-        TRY(run_graphed(s, carry ? s->carry_graphs : s->step_graphs, (uintptr_t)s->Y | (rhs_done ? 1u : 0u), speculative && graphs_on, &replayed, [&]() -> int {
+        TRY(run_graphed(s, carry ? s->carry_graphs : s->step_graphs, (uintptr_t)s->Y | (rhs_done || (carry && carry_slot == 0) ? 1u : 0u), speculative && graphs_on, &replayed, [&]() -> int {
             const int64_t total = (s->n + 1) * (int64_t)s->nv;
             if (!carry) {
                 TRY(newton_step(s, 0, rhs_done));
@@ -1775,7 +1777,7 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
                 TRY(rst_b200_reduce_local(s, 0));
                 newton_trial_dev_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY, s->Yt, s->d_scal, total);
             } else {
-                newton_trial_carry_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY1, s->dY, s->Yt, s->d_scal, total);
+                newton_trial_carry_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY1, s->dY, s->Yt, s->d_scal, total, carry_slot);
             }
             s->launches++;
             set_solution_buffer(s, s->dY1);
@@ -1842,7 +1844,7 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
         st->last_lambda = lambda;
         if (s1 < 1.0 || s1 < s0) {                                // :1962
             accepted = true;
-            if (first_trial_accepted) *first_trial_accepted = speculative && k == 0;
+            if (accepted_slot) *accepted_slot = !speculative ? -1 : (k == 0 ? 1 : 0);   // later trials reduce into slot 0
             break;
         }
         lambda = lambda / std::pow(2.0, (double)k + o->damp_factor); // :1971
@@ -1883,7 +1885,7 @@ extern "C" int rst_b200_newton_solve(rst_b200_solver *s, const rst_b200_newton_o
     bool have_jac = false, recalc = true;
     // carry: the accepted first trial of the previous iteration IS this iteration's undamped step (same y, same factors)
     static const bool carry_on = std::getenv("RST_B200_NO_CARRY") == nullptr;
-    bool carry = false;
+    int carry = -1;     // scalar slot of the accepted trial to carry over, -1: none
     int m = 0, n_jac_reeval = 0, it = 0, status = 0;
     while (it < o->max_iterations) {
         recalc = (!have_jac || m > o->max_jac) ? true : recalc;   // jac_recalc, BVP_utils_damped.rs:185-207
@@ -1892,19 +1894,19 @@ extern "C" int rst_b200_newton_solve(rst_b200_solver *s, const rst_b200_newton_o
             if (rc != RST_B200_OK) { st->status = rc; return rc; }
             have_jac = true;
             m = 0;
-            carry = false;
+            carry = -1;
         }
         m += 1;
         it += 1;
         st->iterations++;
-        bool first_accepted = false;
-        int rc = damped_step(s, o, st, &status, carry && carry_on, &first_accepted);
-        carry = false;
+        int accepted_slot = -1;
+        int rc = damped_step(s, o, st, &status, carry_on ? carry : -1, &accepted_slot);
+        carry = -1;
         if (rc != RST_B200_OK) { st->status = rc; return rc; }
         if (status == 0) {
             TRY(rst_b200_accept_trial(s));
             recalc = false;
-            carry = first_accepted;
+            carry = accepted_slot;
         } else if (status == 1) {
             TRY(rst_b200_accept_trial(s));
             break;

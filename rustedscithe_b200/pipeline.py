@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import time
 
 import numpy as np
 
@@ -82,7 +83,6 @@ class SolvePipeline:
         # Solve i runs on lane i % lanes and the solves take the GPU in the order 0, 1, 2, ...: deterministic, and with
         # world > 1 every rank issues the exchanges of its lanes in the same order (a free-for-all could leave two ranks
         # waiting for each other's OTHER lane).
-        turn = threading.Condition()
         state = {"next": 0}
 
         def lane(k):
@@ -101,16 +101,17 @@ class SolvePipeline:
                         sv.set_params(params[i])
                     _lib.check(L.rst_b200_set_state(sv.handle, src, self.n), L)
                     opts = sv._opts()
-                    with turn:
-                        turn.wait_for(lambda: state["next"] == i or errors)
-                        if errors:
-                            return
+                    # wait for the turn.  A condition variable costs ~0.2 ms per hand-over (waiter wake-up + GIL), during which
+                    # the GPU idles; the other lane sits inside a ctypes call without the GIL, so yielding in a loop is cheap
+                    # and hands over in microseconds
+                    while state["next"] != i and not errors:
+                        time.sleep(0)
+                    if errors:
+                        return
                     try:
                         _lib.check(L.rst_b200_newton_solve(sv.handle, C.byref(opts), C.byref(sv.stats)), L)
                     finally:
-                        with turn:
-                            state["next"] = i + 1
-                            turn.notify_all()
+                        state["next"] = i + 1
                     st = sv.stats
                     stats[i] = (st.status, st.iterations, st.linear_solves, st.jac_recalcs)
                     if st.status == 1:
@@ -121,9 +122,7 @@ class SolvePipeline:
                         else:
                             sols[i] = hout.array.copy()
             except Exception as exc:        # re-raised on the calling thread
-                with turn:
-                    errors.append(exc)
-                    turn.notify_all()
+                errors.append(exc)
 
         threads = [threading.Thread(target=lane, args=(k,)) for k in range(lanes)]
         for t in threads:

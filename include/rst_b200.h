@@ -79,7 +79,7 @@ typedef struct {
     double last_s0, last_s1, last_conv, last_fbound, last_lambda;
     double ms_assemble, ms_factor, ms_solve, ms_total; /* CUDA-event timings, cumulative */
     int solves_reused;         /* of linear_solves (the reference's count): undamped steps taken over, bit for bit, from the accepted
-                                * first trial of the previous iteration (same y, same factors) instead of being recomputed */
+                                * trial of the previous iteration (same y, same factors) instead of being recomputed */
 } rst_b200_newton_stats;
 
 /* scalars of one damping trial, all that crosses PCIe inside the loop */

@@ -70,17 +70,6 @@ __device__ __forceinline__ void sts128_if(bool pred, double *p, double2 v) {
     asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.b32 pp, %3, 0;\n\t@pp st.shared.v2.f64 [%0], {%1, %2};\n\t}"
                  ::"r"((unsigned)__cvta_generic_to_shared(p)), "d"(v.x), "d"(v.y), "r"((int)pred) : "memory");
 }
-// reciprocal without the slow-path subroutine of __drcp_rn: MUFU.RCP64H seed (2^-23) + two Newton steps (~1 ulp).
-// Denormal / zero / non-finite pivots give inf / NaN and are reported through the zero-pivot flag by the caller.
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-}
-
 // part (0 = M, 1 = P, 2 = Q, 3 = padding) of the column pair a lane holds in column tile TC.  nv is a multiple of 4, so a
 // tile crosses at most one part boundary, in its middle: lanes with (lane & 3) < 2 hold the low half.
 template <int NV, int TC>

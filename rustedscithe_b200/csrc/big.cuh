@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(BIGP_THREADS) bigp_forward_kernel(AbdLevel L, 
     if (pvr == 127) L.r_next[slab * nv + t_c] = w;
 }
 
-constexpr int BIGP_CC = 16;      // UEF rows (c) per stage in the backward sweep
+constexpr int BIGP_CC = 16;      // UEF rows (c) per stage in the backward sweep (must divide 32: a chunk's unknowns live in one warp)
 __host__ __device__ inline size_t bigp_backward_smem(int nv) { return (size_t)BIGP_NS * BIGP_CC * nv * sizeof(double); }
 
 // backward sweep: interior nodes of the slab from its end nodes.  Stage order per block row (descending):
@@ -726,14 +726,25 @@ __global__ void __launch_bounds__(BIGP_THREADS) bigp_backward_kernel(AbdLevel L,
             const int c0 = ch * BIGP_CC, cc = min(BIGP_CC, nv - c0);
             if (grp == 0) {
                 const double *tile = ring + (size_t)slot * stage_doubles + k;
-                for (int cl = cc - 1; cl >= 0; --cl) {
-                    const int kk = c0 + cl;
-                    if (k == kk) xb[kk & 1] = t / tile[cl * nv];
-                    asm volatile("bar.sync 1, 64;" ::: "memory");
-                    const double x = xb[kk & 1];
-                    if (k == kk) Yn[kk] = x;
-                    else if (k < kk) t = fma(-tile[cl * nv], x, t);
+                // the reciprocal of this thread's diagonal entry is formed when its chunk arrives, off the serial chain below
+                // (a division there costs more than the barrier + FMA of a substitution step)
+                double myinv = 0.0;
+                if (k >= c0 && k < c0 + cc) myinv = fast_rcp(tile[(k - c0) * nv]);
+                // the chunk's <= 16 unknowns sit in one warp (BIGP_CC = 16 divides 32): their triangular solve runs on shuffles,
+                // no barrier and no shared-memory round trip per unknown; the threads below the chunk apply the chunk's
+                // unknowns afterwards in the same order (same rounding as updating step by step)
+                const bool in_chunk = k >= c0 && k < c0 + cc;
+                if ((k >> 5) == (c0 >> 5)) {
+                    for (int cl = cc - 1; cl >= 0; --cl) {
+                        const int kk = c0 + cl;
+                        const double x = __shfl_sync(RST_FULL_MASK, t * myinv, kk & 31);
+                        if (k == kk) Yn[kk] = x;
+                        else if (in_chunk && k < kk) t = fma(-tile[cl * nv], x, t);
+                    }
                 }
+                asm volatile("bar.sync 1, 64;" ::: "memory");
+                if (k < c0)
+                    for (int cl = cc - 1; cl >= 0; --cl) t = fma(-tile[cl * nv], Yn[c0 + cl], t);
             }
             __syncthreads();
             if (tid == 0 && sidx + BIGP_NS < total) issue(sidx + BIGP_NS);

@@ -46,4 +46,16 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 
+// reciprocal without the slow-path subroutine of __drcp_rn: MUFU.RCP64H seed (2^-23) + two Newton steps (~1 ulp).
+// Denormal / zero / non-finite pivots give inf / NaN and are reported through the zero-pivot flag by the caller.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+
 }  // namespace rst

@@ -480,6 +480,18 @@ __global__ void __launch_bounds__(BigdCfg::THREADS + 128, 1) bigd_factor_kernel(
 #ifdef BIGD_TIMING
             const long long tu2 = clock64();
 #endif
+#if !defined(BIGD_X_NOWRITE) && !defined(BIGD_X_WRITE_AT_END)
+            // U | E | F of the PREVIOUS block row leave shared memory here, two of its 24 store rounds per block, in the time the
+            // update warps would otherwise spend waiting for the panel warps (the staging buffer is rewritten after block 15)
+            if (istep > 1 && b < 3 * NV * NV / C::THREADS / 2) {
+                double *uef = L.UEF + (g - 1) * (int64_t)(3 * NV * NV);
+#pragma unroll
+                for (int m = 2 * b; m < 2 * b + 2; ++m) {
+                    const int idx = tid + C::THREADS * m;      // = c * 64 + k
+                    st_cs(uef + idx, sm.ust[idx & (NV - 1)][idx >> 6]);
+                }
+            }
+#endif
             if (more) bar_named(1, ALL);   // B(b + 1)
 #ifdef BIGD_TIMING
             t_serial += tu1 - tu0; t_dmma += tu2 - tu1; t_waitb += clock64() - tu2;
@@ -503,7 +515,10 @@ __global__ void __launch_bounds__(BigdCfg::THREADS + 128, 1) bigd_factor_kernel(
             if (lane == 0) sm.masks[warp] = mf;
         }
         bar_named(2, UPD);
-#ifndef BIGD_X_NOWRITE
+#if !defined(BIGD_X_NOWRITE)
+#if !defined(BIGD_X_WRITE_AT_END)
+        if (istep == len - 1)      // the last block row of the slab has no successor to hide its write-out behind
+#endif
         {
             double *uef = L.UEF + g * (int64_t)(3 * NV * NV);
 #pragma unroll 4

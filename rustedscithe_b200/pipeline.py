@@ -83,7 +83,7 @@ class SolvePipeline:
         # Solve i runs on lane i % lanes and the solves take the GPU in the order 0, 1, 2, ...: deterministic, and with
         # world > 1 every rank issues the exchanges of its lanes in the same order (a free-for-all could leave two ranks
         # waiting for each other's OTHER lane).
-        state = {"next": 0}
+        state = {"next": 0, "first_copies": 0}
 
         def lane(k):
             sv, hin, hout = self.solvers[k], self._in[k], self._out[k]
@@ -99,7 +99,15 @@ class SolvePipeline:
                         src = hin.ptr
                     if params is not None:
                         sv.set_params(params[i])
-                    _lib.check(L.rst_b200_set_state(sv.handle, src, self.n), L)
+                    # the first copies of a batch go one after the other (lane 0 first): sharing PCIe between them would only
+                    # delay the first solve
+                    while i < lanes and state["first_copies"] != i and not errors:
+                        time.sleep(0)
+                    try:
+                        _lib.check(L.rst_b200_set_state(sv.handle, src, self.n), L)
+                    finally:
+                        if i < lanes:
+                            state["first_copies"] = i + 1
                     opts = sv._opts()
                     # wait for the turn.  A condition variable costs ~0.2 ms per hand-over (waiter wake-up + GIL), during which
                     # the GPU idles; the other lane sits inside a ctypes call without the GIL, so yielding in a loop is cheap

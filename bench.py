@@ -16,7 +16,15 @@ Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` prints ONE 
     Compact results of the other configurations ride along under ``secondary`` (``--no-secondary`` skips them).
   * ``value``   : iterations/s, state resident in HBM (CUDA events on the launching stream, max over ranks)
   * ``e2e``     : the same through the host-buffer C-ABI calls a Rust host would make per solve
-                  (rst_b200_set_state H2D -> rst_b200_newton_solve -> rst_b200_get_state D2H)
+                  (rst_b200_set_state H2D -> rst_b200_newton_solve -> rst_b200_get_state D2H, pinned host vectors, both copies
+                  of every solve inside the timed region).  ``e2e.value`` runs the solves on two handles / host threads per
+                  rank (rustedscithe_b200.pipeline.SolvePipeline: one solve's copies under the other's kernels, results checked
+                  against the one-handle answer before timing); ``e2e.one_handle_value`` is the plain sequence on one handle
+                  (``--no-pipeline`` reports only that).
+  * ``config.per_solve``: the reference's counters of one solve; ``linear_solves_executed`` of the counted ``linear_solves``
+                  were run, the others are the accepted trial of the previous iteration taken over bit for bit.
+  * ``kernels`` : per-phase launch times with the L2 flushed before each (assemble_FJ, assemble_F, factor, solve, and
+                  factor_solve = the factorisation + first solve in one call, which is what follows every new Jacobian)
   * ``roofline``: dominant kernel of the solve, algorithmic bytes / measured launch duration
                   vs MEASURED_PEAKS.json hbm_gbs; ``traffic`` = ncu dram bytes of the committed capture (profiles/)
   * ``cpu_baseline`` / ``--impl reference``: the CPU oracle (port of the reference's path with its

@@ -227,23 +227,19 @@ __global__ void __launch_bounds__(256) newton_trial_dev_kernel(const double *__r
         Yt[idx] = Y[idx] - dY[idx] * lambda;
 }
 
-// First trial of an iteration whose undamped step is ALREADY KNOWN: when the previous iteration accepted its first trial
-// (state Yt, step dY1 = J^-1 F(Yt), scalars in slot 1) and the Jacobian is kept, the reference's next iteration recomputes
-// F(y) and J^-1 F(y) at y = Yt with the same factors (NR_Damp_solver_damped.rs:1862-1880) -- bit for bit the trial's dY1.
-// This kernel takes them over instead: dY <- dY1, scalars slot 0 <- slot 1, Yt = Y - lambda dY with lambda = fbound.
-// src_slot: where the accepted trial's scalars are -- slot 1 after a speculative first trial (copied to slot 0 here), slot 0
-// after a later trial of the damping loop (already in place).
-__global__ void __launch_bounds__(256) newton_trial_carry_kernel(const double *__restrict__ Y, const double *__restrict__ dY1,
-                                                                 double *__restrict__ dY, double *__restrict__ Yt,
-                                                                 double *__restrict__ scal, int64_t total, int src_slot) {
+// First trial of an iteration whose undamped step is ALREADY KNOWN: when the previous iteration accepted a trial (state Yt, step
+// dY1 = J^-1 F(Yt)) and the Jacobian is kept, the reference's next iteration recomputes F(y) and J^-1 F(y) at y = Yt with the same
+// factors (NR_Damp_solver_damped.rs:1862-1880) -- bit for bit the trial's dY1.  The host takes it over by swapping the roles of the
+// two step buffers (so `step` below IS the accepted trial's step); this kernel forms the next trial state from it and moves the
+// accepted trial's scalars into slot 0 when they are in slot 1 (speculative first trial; a later trial reduces into slot 0).
+__global__ void __launch_bounds__(256) newton_trial_carry_kernel(const double *__restrict__ Y, const double *__restrict__ step,
+                                                                 double *__restrict__ Yt, double *__restrict__ scal, int64_t total,
+                                                                 int src_slot) {
     const double lambda = 1.0 * scal[8 * src_slot + 2];
     if (src_slot == 1 && blockIdx.x == 0 && threadIdx.x < 8) scal[threadIdx.x] = scal[8 + threadIdx.x];   // nobody reads slot 0 in this kernel
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const double d = dY1[idx];
-        dY[idx] = d;
-        Yt[idx] = Y[idx] - d * lambda;
-    }
+         idx += (int64_t)gridDim.x * blockDim.x)
+        Yt[idx] = Y[idx] - step[idx] * lambda;
 }
 
 // ---- reduced ordering <-> full node-major state (numeric_discretization.rs:80-106, BVP_utils.rs:534-558) ----

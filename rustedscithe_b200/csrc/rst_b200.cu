@@ -387,6 +387,7 @@ struct rst_b200_solver {
     // device buffers
     double *Y = nullptr, *Yt = nullptr, *F = nullptr, *A = nullptr, *B = nullptr, *dY = nullptr;
     double *d_mesh = nullptr, *d_params = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_rtol = nullptr;
+    double *dY_home = nullptr; // the buffer the undamped step starts in (dY and dY1 swap roles when a step is carried over)
     double *Y_home = nullptr; // the buffer Y starts in: the Newton drivers begin every solve there (stable CUDA-graph keys)
     double *dY1 = nullptr;    // step of a damping trial (the undamped step in dY must survive rejected trials)
     double *sol = nullptr;    // buffer the linear solve currently writes to (dY or dY1)
@@ -659,6 +660,7 @@ extern "C" int rst_b200_create(const rst_b200_desc *d, rst_b200_solver **out) {
         s->Y_home = s->Y;
         TRY(dev_alloc(s, &s->Yt, nodes));
         TRY(dev_alloc(s, &s->dY, nodes));
+        s->dY_home = s->dY;
         TRY(dev_alloc(s, &s->dY1, nodes));
         s->sol = s->dY;
         TRY(dev_alloc(s, &s->F, (size_t)n * nv));
@@ -1660,6 +1662,15 @@ static void set_solution_buffer(rst_b200_solver *s, double *buf) {
     }
 }
 
+// dY and dY1 swap roles whenever an accepted trial is carried into the next iteration; drivers that cache launch sequences by the
+// state buffer only (frozen loop) and every new Newton solve start from the home assignment (the contents are dead by then)
+static void normalize_step_buffers(rst_b200_solver *s) {
+    if (s->dY != s->dY_home) {
+        std::swap(s->dY, s->dY1);
+        set_solution_buffer(s, s->dY);
+    }
+}
+
 // ---- damped Newton -------------------------------------------------------------------------------
 static int check_scalars(const rst_b200_scalars &sc) {
     if (sc.nan_flag != 0.0 || (((unsigned)sc.device_flags) & RST_FLAG_NAN_F))
@@ -1763,13 +1774,15 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
     carry = carry && speculative;
     const bool rhs_done = s->rhs_in_factors && !carry;   // first solve after recalc_jacobian: no residual pass, no forward sweeps
     s->rhs_in_factors = false;
+    if (carry) std::swap(s->dY, s->dY1);                 // the accepted trial's step IS this iteration's undamped step
+    const uintptr_t step_parity = s->dY != s->dY_home ? 2u : 0u;   // the graphs bake the buffer addresses in
     s->scal_slot = 0;
     // The speculative sequence is ~25-45 launches with fixed arguments: small meshes are launch bound, so it is captured
     // into a CUDA graph (per Y / Y_trial parity) the second time it runs and replayed with one launch afterwards.
     const bool graphs_on = std::getenv("RST_B200_NO_GRAPH") == nullptr;   // read per call: tests toggle it
     {
         bool replayed = false;
-        TRY(run_graphed(s, carry ? s->carry_graphs : s->step_graphs, (uintptr_t)s->Y | (rhs_done || (carry && carry_slot == 0) ? 1u : 0u), speculative && graphs_on, &replayed, [&]() -> int {
+        TRY(run_graphed(s, carry ? s->carry_graphs : s->step_graphs, (uintptr_t)s->Y | step_parity | (rhs_done || (carry && carry_slot == 0) ? 1u : 0u), speculative && graphs_on, &replayed, [&]() -> int {
             const int64_t total = (s->n + 1) * (int64_t)s->nv;
             if (!carry) {
                 TRY(newton_step(s, 0, rhs_done));
@@ -1777,7 +1790,7 @@ static int damped_step(rst_b200_solver *s, const rst_b200_newton_opts *o, rst_b2
                 TRY(rst_b200_reduce_local(s, 0));
                 newton_trial_dev_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY, s->Yt, s->d_scal, total);
             } else {
-                newton_trial_carry_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY1, s->dY, s->Yt, s->d_scal, total, carry_slot);
+                newton_trial_carry_kernel<<<s->red_blocks, 256, 0, s->stream>>>(s->Y, s->dY, s->Yt, s->d_scal, total, carry_slot);
             }
             s->launches++;
             set_solution_buffer(s, s->dY1);
@@ -1878,6 +1891,7 @@ extern "C" int rst_b200_newton_solve(rst_b200_solver *s, const rst_b200_newton_o
     // Y and Y_trial swap roles with every accepted iteration, and the CUDA-graph caches are keyed by the buffer Y lives in: after
     // a solve with an odd number of iterations the next one would meet every key in its other flavour (and pay the captures a
     // second time).  Start every solve from the home buffer: one device-to-device copy of the state when the roles are swapped.
+    normalize_step_buffers(s);
     if (s->Y != s->Y_home && s->Yt == s->Y_home) {
         CUDA_TRY(cudaMemcpyAsync(s->Y_home, s->Y, (size_t)(s->n + 1) * s->nv * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
         std::swap(s->Y, s->Yt);
@@ -1943,6 +1957,7 @@ static bool frozen_recalc(const rst_b200_frozen_opts *o, bool have_jac, int m, d
 extern "C" int rst_b200_newton_frozen(rst_b200_solver *s, const rst_b200_frozen_opts *o, rst_b200_newton_stats *st) {
     if (!s || !o || !st) return fail(RST_B200_ERR_INVALID, "null argument");
     if (o->strategy < 0 || o->strategy > RST_B200_FROZEN_COMPLEX) return fail(RST_B200_ERR_INVALID, "unknown strategy");
+    normalize_step_buffers(s);
     std::memset(st, 0, sizeof(*st));
     const auto t_begin = std::chrono::steady_clock::now();
     bool jac_recalc = true, have_jac = false;
